@@ -1,0 +1,200 @@
+/*
+ * ref_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * extern "C" probe around the UNMODIFIED reference objects.  oracle/build_ref.py compiles
+ * this file once per code variant as a single translation unit: it first includes a copy
+ * of ArrayLDPCMacro.h whose compile-time enum (ArrayLDPCMacro.h:18-24, G_mlist :192-196)
+ * was switched to the variant (generated into a temp dir, never stored in the repo), then
+ * pulls in the reference sources where they lie (REF_DIR = /root/reference); their own
+ * `#include "ArrayLDPCMacro.h"` is a no-op because of the include guard.
+ * Output: oracle/_ref/libref_<variant>.so.  Nothing here restates reference logic: every
+ * entry point forwards to a reference member function.
+ */
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <bitset>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#define private public
+#include "ArrayLDPCMacro.h" /* the variant header, found first on the -I path */
+#undef private
+
+#define REF_STR2(x) #x
+#define REF_STR(x) REF_STR2(x)
+#define REF_FILE(name) REF_STR(REF_DIR/name)
+
+#include REF_FILE(rngs.cpp)
+#include REF_FILE(rvgs.cpp)
+#include REF_FILE(ArrayLDPC_Decoder.cpp)
+#include REF_FILE(ArrayLDPC_Encoder.cpp)
+
+static FP_Decoder *g_dec = 0;
+static FP_Encoder *g_enc = 0;
+
+static FP_Decoder &dec()
+{
+    if (!g_dec) g_dec = new FP_Decoder;
+    return *g_dec;
+}
+
+extern "C" {
+
+/* compile-time dimensions of this variant */
+void ref_dims(int *out)
+{
+    out[0] = NUM_VAR; out[1] = NUM_CHK; out[2] = CHK_DEG; out[3] = VAR_DEG;
+    out[4] = INFO_LENGTH; out[5] = P; out[6] = NUM_CGRP; out[7] = NUM_VGRP;
+    out[8] = MAX_ITER; out[9] = FRAC_WIDTH; out[10] = RAM_DEPTH;
+}
+
+/* FP_Decoder::ReadH opens "H_802.11_IndZero.txt" in the CWD (ArrayLDPC_Decoder.cpp:646). */
+void ref_read_h(const char *dir)
+{
+    char cwd[4096];
+    if (!getcwd(cwd, sizeof cwd)) return;
+    if (chdir(dir) != 0) return;
+    dec().ReadH();
+    if (chdir(cwd) != 0) return;
+}
+
+/* fill the private tables directly (bypasses the hard-coded file name) */
+void ref_set_tables(const int *vdeg, const int *cdeg, const int *vlist, int vstride,
+                    const int *clist, int cstride)
+{
+    FP_Decoder &d = dec();
+    d.vnum = NUM_VAR; d.cnum = NUM_CHK;
+    for (int v = 0; v < NUM_VAR; ++v) {
+        d.vdeg[v] = vdeg[v];
+        for (int j = 0; j < vdeg[v]; ++j) d.vlist[v][j] = vlist[v * vstride + j];
+    }
+    for (int c = 0; c < NUM_CHK; ++c) {
+        d.cdeg[c] = cdeg[c];
+        for (int k = 0; k < cdeg[c]; ++k) d.clist[c][k] = clist[c * cstride + k];
+    }
+}
+
+void ref_get_tables(int *vdeg, int *cdeg, int *vlist, int *clist)
+{
+    FP_Decoder &d = dec();
+    for (int v = 0; v < NUM_VAR; ++v) {
+        vdeg[v] = d.vdeg[v];
+        for (int j = 0; j < VAR_DEG; ++j) vlist[v * VAR_DEG + j] = j < d.vdeg[v] ? d.vlist[v][j] : -1;
+    }
+    for (int c = 0; c < NUM_CHK; ++c) {
+        cdeg[c] = d.cdeg[c];
+        for (int k = 0; k < CHK_DEG; ++k) clist[c * CHK_DEG + k] = k < d.cdeg[c] ? d.clist[c][k] : -1;
+    }
+}
+
+static void dump_state(int *bits, int *post, int *edge)
+{
+    FP_Decoder &d = dec();
+    if (bits) for (int v = 0; v < CWD_LENGTH; ++v) bits[v] = d.DecodedCodeword[v];
+    if (post) for (int v = 0; v < CWD_LENGTH; ++v) post[v] = d.Posteriori_fp[v];
+    if (edge)
+        for (int k = 0; k < CHK_DEG; ++k)
+            for (int c = 0; c < RAM_DEPTH; ++c) edge[k * RAM_DEPTH + c] = d.EdgeRAM[k].BRAM_fp[c];
+}
+
+int ref_decode_general_fp(const int *llr, int *bits, int *post, int *edge)
+{
+    int it = dec().decode_general_fp(llr);
+    dump_state(bits, post, edge);
+    return it;
+}
+
+/* set_pcv != 0 reproduces the drivers' setState(PCV) before every frame (PerfTest.cpp:180) */
+int ref_decode_fixpoint(const int *llr, int set_pcv, int *bits, int *post, int *edge)
+{
+    if (set_pcv) dec().setState(PCV);
+    int it = dec().decode_fixpoint(llr);
+    dump_state(bits, post, edge);
+    return it;
+}
+
+int ref_get_state(void) { return dec().getState(); }
+void ref_set_state(int s) { dec().setState(s); }
+int ref_sxor(int x, int y) { return dec().sxor(x, y); }
+double ref_rate(void) { return dec().getRate(); }
+int ref_hard_decision(const int *llr) { return dec().hardDecision(llr); }
+
+void ref_sxor_grid(int lo, int hi, int *out)
+{
+    FP_Decoder &d = dec();
+    for (int x = lo; x <= hi; ++x)
+        for (int y = lo; y <= hi; ++y) *out++ = d.sxor(x, y);
+}
+
+/* throughput loop with DecodeTrial semantics (PerfTest.cpp:178-182) */
+long ref_decode_many(const int *llr, long frames, int fixpoint, int *iters)
+{
+    FP_Decoder &d = dec();
+    long total = 0;
+    for (long f = 0; f < frames; ++f) {
+        int it;
+        if (fixpoint) { d.setState(PCV); it = d.decode_fixpoint(llr + f * CWD_LENGTH); }
+        else it = d.decode_general_fp(llr + f * CWD_LENGTH);
+        if (iters) iters[f] = it;
+        total += it;
+    }
+    return total;
+}
+
+/* RNG / variates (rngs.cpp, rvgs.cpp) */
+double ref_random(void) { return Random(); }
+double ref_normal(double m, double s) { return Normal(m, s); }
+void ref_put_seed(long x) { PutSeed(x); }
+long ref_get_seed(void) { long x; GetSeed(&x); return x; }
+
+/* the drivers' channel line (PerfTest.cpp:112,119): evaluated here so the expression is
+ * compiled exactly as the reference compiles it */
+void ref_channel_frame(const int *codeword, double snr, double sigma, int *llr_fp)
+{
+    double LLR;
+    for (int i = 0; i < CWD_LENGTH; ++i) {
+        LLR = 2 * snr * (1 - 2 * (codeword ? codeword[i] : 0) + Normal(0, sigma));
+        llr_fp[i] = int(LLR * (1 << FRAC_WIDTH));
+    }
+}
+
+/* encoder (ArrayLDPC_Encoder.cpp) */
+int ref_encoder_open(const char *path)
+{
+    std::ifstream probe(path);
+    if (!probe) return -1; /* the reference would print and exit(0) */
+    delete g_enc;
+    g_enc = new FP_Encoder(const_cast<char *>(path), 0);
+    return 0;
+}
+void ref_encode(const char *info, int len, int *codeword, int *info_index)
+{
+    /* the two-argument overload is the one every driver loop uses (PerfTest.cpp:89,283) */
+    char *buf = new char[len];
+    memcpy(buf, info, len);
+    g_enc->encode(buf, len);
+    for (int v = 0; v < NUM_VAR; ++v) codeword[v] = g_enc->getCodeword(v);
+    for (int i = 0; i < INFO_LENGTH; ++i) info_index[i] = g_enc->getInfoIndex(i);
+    delete[] buf;
+}
+
+/* BER bookkeeping (ArrayLDPC_Decoder.cpp:178-206, 698-722) */
+void ref_set_info(const char *info, int len, const int *info_index)
+{
+    char *buf = new char[len];
+    memcpy(buf, info, len);
+    dec().setInfoBit(buf, len);
+    dec().setInfoIndex(const_cast<int *>(info_index));
+    delete[] buf;
+}
+int ref_calculate_ber(void)
+{
+    dec().resetBER();
+    return dec().calculateBER();
+}
+
+} /* extern "C" */
