@@ -1,0 +1,234 @@
+"""ctypes binding of libldpc_b200.so (include/ldpc_capi.h).
+
+Thin by design: the product is the CUDA library; Python only moves pointers.  Importing this
+module never falls back to a CPU implementation -- if the shared library is missing or no CUDA
+device is present the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libldpc_b200.so")
+
+FMT_AUTO, FMT_A, FMT_C = 0, 1, 3
+OK, ERR_IO, ERR_FORMAT, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5, -6, -7
+
+# every symbol include/ldpc_capi.h declares
+EXPORTS = (
+    "ldpc_strerror", "ldpc_last_error", "ldpc_code_load", "ldpc_code_from_checks", "ldpc_code_array",
+    "ldpc_code_free", "ldpc_code_dims", "ldpc_code_tables", "ldpc_code_rate", "ldpc_code_save",
+    "ldpc_decoder_cfg_default", "ldpc_decoder_create", "ldpc_decoder_destroy", "ldpc_decode_batch",
+    "ldpc_decode_batch_device", "ldpc_decoder_sync", "ldpc_decoder_get_stats", "ldpc_device_count",
+)
+
+
+class LdpcError(RuntimeError):
+    def __init__(self, status, detail):
+        self.status = status
+        super().__init__("ldpc status %d (%s): %s" % (status, _strerror(status), detail))
+
+
+class DecoderCfg(C.Structure):
+    _fields_ = [("max_iter", C.c_int), ("precheck", C.c_int), ("device", C.c_int), ("precision", C.c_int),
+                ("threads", C.c_int), ("frames_per_cta", C.c_int)]
+
+
+class DecoderStats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("frames", C.c_uint64), ("fallback_frames", C.c_uint64),
+                ("threads", C.c_int), ("threads32", C.c_int), ("frames_per_cta", C.c_int),
+                ("frames_per_cta32", C.c_int), ("grid", C.c_int), ("smem_bytes", C.c_int),
+                ("smem_bytes32", C.c_int)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libldpc_b200.so is not built: run `python -m fixedpointldpc_b200.build` "
+                           "(or __graft_entry__.build())")
+    L = C.CDLL(LIB_PATH)
+    vp, ip = C.c_void_p, C.POINTER(C.c_int)
+    L.ldpc_strerror.restype = C.c_char_p
+    L.ldpc_strerror.argtypes = [C.c_int]
+    L.ldpc_last_error.restype = C.c_char_p
+    L.ldpc_code_load.restype = vp
+    L.ldpc_code_load.argtypes = [C.c_char_p, C.c_int, ip]
+    L.ldpc_code_from_checks.restype = vp
+    L.ldpc_code_from_checks.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, ip]
+    L.ldpc_code_array.restype = vp
+    L.ldpc_code_array.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, ip]
+    L.ldpc_code_free.argtypes = [vp]
+    L.ldpc_code_dims.argtypes = [vp, ip, ip, ip, ip, ip]
+    L.ldpc_code_tables.argtypes = [vp, vp, vp, vp, vp]
+    L.ldpc_code_rate.restype = C.c_double
+    L.ldpc_code_rate.argtypes = [vp]
+    L.ldpc_code_save.argtypes = [vp, C.c_char_p]
+    L.ldpc_decoder_cfg_default.argtypes = [C.POINTER(DecoderCfg)]
+    L.ldpc_decoder_create.restype = vp
+    L.ldpc_decoder_create.argtypes = [vp, C.POINTER(DecoderCfg), ip]
+    L.ldpc_decoder_destroy.argtypes = [vp]
+    L.ldpc_decode_batch.argtypes = [vp, vp, C.c_size_t, vp, vp, vp, vp]
+    L.ldpc_decode_batch_device.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, vp, vp, vp, vp]
+    L.ldpc_decoder_sync.argtypes = [vp]
+    L.ldpc_decoder_get_stats.argtypes = [vp, C.POINTER(DecoderStats)]
+    L.ldpc_device_count.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _strerror(status):
+    return load_library().ldpc_strerror(status).decode()
+
+
+def _check(status):
+    if status != OK:
+        raise LdpcError(status, load_library().ldpc_last_error().decode())
+
+
+def _ptr(arr):
+    return None if arr is None else arr.ctypes.data
+
+
+class Code:
+    """Parity-check tables of one code (host).  Mirrors what FP_Decoder::ReadH fills
+    (ArrayLDPC_Decoder.cpp:642-674) with runtime dimensions."""
+
+    def __init__(self, handle):
+        self._h = handle
+        L = load_library()
+        v = [C.c_int() for _ in range(5)]
+        _check(L.ldpc_code_dims(self._h, *[C.byref(x) for x in v]))
+        self.n, self.m, self.edges, self.dc_max, self.dv_max = (x.value for x in v)
+        self.nw32 = (self.n + 31) // 32
+
+    @classmethod
+    def load(cls, path, fmt=FMT_AUTO):
+        L = load_library()
+        err = C.c_int()
+        h = L.ldpc_code_load(os.fsencode(path), fmt, C.byref(err))
+        if not h:
+            _check(err.value)
+        return cls(h)
+
+    @classmethod
+    def from_checks(cls, n, cdeg, clist):
+        L = load_library()
+        cdeg = np.ascontiguousarray(cdeg, np.int32)
+        clist = np.ascontiguousarray(clist, np.int32)
+        err = C.c_int()
+        h = L.ldpc_code_from_checks(n, len(cdeg), _ptr(cdeg), _ptr(clist), clist.shape[1], C.byref(err))
+        if not h:
+            _check(err.value)
+        return cls(h)
+
+    @classmethod
+    def array(cls, p, nrows, ncols=None, row_mult=None, col_sel=None, backward=False):
+        L = load_library()
+        ncols = p if ncols is None else ncols
+        rm = None if row_mult is None else np.ascontiguousarray(row_mult, np.int32)
+        cs = None if col_sel is None else np.ascontiguousarray(col_sel, np.int32)
+        err = C.c_int()
+        h = L.ldpc_code_array(p, nrows, _ptr(rm), ncols, _ptr(cs), int(backward), C.byref(err))
+        if not h:
+            _check(err.value)
+        return cls(h)
+
+    def tables(self):
+        vdeg = np.zeros(self.n, np.int32); cdeg = np.zeros(self.m, np.int32)
+        vlist = np.zeros((self.n, self.dv_max), np.int32); clist = np.zeros((self.m, self.dc_max), np.int32)
+        _check(load_library().ldpc_code_tables(self._h, _ptr(vdeg), _ptr(cdeg), _ptr(vlist), _ptr(clist)))
+        return vdeg, cdeg, vlist, clist
+
+    @property
+    def rate(self):
+        return load_library().ldpc_code_rate(self._h)
+
+    def save(self, path):
+        _check(load_library().ldpc_code_save(self._h, os.fsencode(path)))
+
+    def close(self):
+        if self._h:
+            load_library().ldpc_code_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Decoder:
+    """Batched FP_Decoder::decode_general_fp (precheck=False) / decode_fixpoint (precheck=True)."""
+
+    def __init__(self, code, max_iter=30, precheck=False, device=0, precision=0, threads=0, frames_per_cta=0):
+        L = load_library()
+        self.code = code
+        cfg = DecoderCfg()
+        L.ldpc_decoder_cfg_default(C.byref(cfg))
+        cfg.max_iter, cfg.precheck, cfg.device, cfg.precision = max_iter, int(precheck), device, precision
+        cfg.threads, cfg.frames_per_cta = threads, frames_per_cta
+        err = C.c_int()
+        self._h = L.ldpc_decoder_create(code._h, C.byref(cfg), C.byref(err))
+        if not self._h:
+            _check(err.value)
+
+    def decode(self, llr, want_bits=True, want_post=False, want_v2c=False):
+        """llr: int32 [frames][n] host array.  Returns dict(iters, bits, post, v2c)."""
+        c = self.code
+        llr = np.ascontiguousarray(llr, np.int32).reshape(-1, c.n)
+        f = len(llr)
+        out = {"iters": np.zeros(f, np.int32),
+               "bits": np.zeros((f, c.nw32), np.uint32) if want_bits else None,
+               "post": np.zeros((f, c.n), np.int32) if want_post else None,
+               "v2c": np.zeros((f, c.dc_max, c.m), np.int32) if want_v2c else None}
+        _check(load_library().ldpc_decode_batch(self._h, _ptr(llr), f, _ptr(out["iters"]), _ptr(out["bits"]),
+                                                _ptr(out["post"]), _ptr(out["v2c"])))
+        return out
+
+    def decode_raw(self, llr_ptr, frames, iters_ptr, bits_ptr=None, post_ptr=None, v2c_ptr=None):
+        """Host-pointer call (pinned buffers for the end-to-end timing)."""
+        _check(load_library().ldpc_decode_batch(self._h, llr_ptr, frames, iters_ptr, bits_ptr, post_ptr, v2c_ptr))
+
+    def decode_device(self, llr_ptr, llr_bits, frames, iters_ptr, bits_ptr=None, post_ptr=None, v2c_ptr=None,
+                      stream=None):
+        """Device-pointer call, asynchronous on `stream` (raw cudaStream_t value or None)."""
+        _check(load_library().ldpc_decode_batch_device(self._h, llr_ptr, llr_bits, frames, iters_ptr, bits_ptr,
+                                                       post_ptr, v2c_ptr, stream))
+
+    def sync(self):
+        _check(load_library().ldpc_decoder_sync(self._h))
+
+    def stats(self):
+        s = DecoderStats()
+        _check(load_library().ldpc_decoder_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in DecoderStats._fields_}
+
+    def close(self):
+        if self._h:
+            load_library().ldpc_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def unpack_bits(bits, n):
+    """[frames][nw32] uint32 -> [frames][n] 0/1 ints (bit v%32 of word v/32)."""
+    b = np.ascontiguousarray(bits, np.uint32)
+    out = ((b[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(len(b), -1)
+    return out[:, :n].astype(np.int32)
+
+
+def device_count():
+    return load_library().ldpc_device_count()

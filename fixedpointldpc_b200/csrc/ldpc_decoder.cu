@@ -1,0 +1,420 @@
+// ldpc_decoder.cu -- device-resident decode engine behind the C ABI (include/ldpc_capi.h).
+//
+// Owns the device copies of the code tables, picks the kernel instantiation and launch shape
+// for the code, and runs the packed int16x2 kernel with an exact int32 re-decode of the
+// frames whose values left the packed guard range.  There is no CPU decode path here.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ldpc_capi.h"
+#include "ldpc_code.hpp"
+#include "ldpc_kernels.cuh"
+
+namespace ldpc {
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            ldpc::set_error(std::string(#expr) + ": " + cudaGetErrorString(e_));                 \
+            return LDPC_ERR_CUDA;                                                          \
+        }                                                                                  \
+    } while (0)
+
+typedef void (*kernel_fn)(const KParams);
+
+struct KernelChoice {
+    kernel_fn fn = nullptr;
+    int max_threads = 0;
+};
+
+template <class T, int DC, bool REG, int DV> static KernelChoice make_choice()
+{
+    KernelChoice k;
+    k.fn = decode_kernel<T, DC, REG, DV>;
+    k.max_threads = LaunchShape<DC>::MAX_THREADS;
+    return k;
+}
+
+// Exact instantiations for the four named codes plus a generic bucket.
+template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
+{
+    bool regular = true;
+    for (int d : c.cdeg) regular &= (d == c.dc_max);
+    if (regular && c.dc_max == 47 && c.dv_max <= 5) return make_choice<T, 47, true, 5>();    // array p47 r5
+    if (regular && c.dc_max == 47 && c.dv_max <= 24) return make_choice<T, 47, true, 24>();  // array p47 r24
+    if (regular && c.dc_max == 28 && c.dv_max <= 4) return make_choice<T, 28, true, 4>();    // cut79
+    if (c.dc_max <= 8 && c.dv_max <= 12) return make_choice<T, 8, false, 12>();              // 802.11n 1944 r1/2
+    if (c.dc_max <= 64 && c.dv_max <= 32) return make_choice<T, 64, false, 32>();
+    return KernelChoice();
+}
+
+struct Plan {
+    KernelChoice kernel;
+    int W = 0, threads = 0, smem = 0;
+};
+
+}  // namespace ldpc
+
+using namespace ldpc;
+
+struct ldpc_decoder {
+    ldpc_code code;
+    ldpc_decoder_cfg cfg;
+    int device = 0, sm_count = 0, max_smem = 0;
+    cudaStream_t stream = nullptr;
+    // device tables
+    uint8_t *d_cdeg = nullptr, *d_vdeg = nullptr;
+    uint16_t *d_vedge = nullptr;
+    unsigned long long *d_queue = nullptr;  // [2]: packed launch, int32 launch
+    Plan plan16, plan32;
+    // host-buffer path staging
+    void *d_llr = nullptr; int *d_iters = nullptr; uint32_t *d_bits = nullptr; int *d_post = nullptr; int *d_v2c = nullptr;
+    size_t cap_frames = 0; bool cap_post = false, cap_v2c = false;
+    // frames flagged by the packed kernel: list, length of the current call, running total
+    int *d_fb_index = nullptr, *d_fb_count = nullptr;
+    unsigned long long *d_fb_total = nullptr;
+    size_t fb_cap = 0;
+    ldpc_decoder_stats stats;
+};
+
+namespace ldpc {
+
+static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_threads, int want_slots, Plan &out)
+{
+    const ldpc_code &c = d.code;
+    if (!k.fn) { set_error("check degree > 64 or variable degree > 32: no kernel instantiation"); return LDPC_ERR_UNSUPPORTED; }
+    if (c.edges > 65535) { set_error("more than 65535 edges"); return LDPC_ERR_UNSUPPORTED; }
+    const int per_w = (c.edges + c.n) * 4;
+    const int budget = d.max_smem - (int)sizeof(Ctrl) - 64;
+    int W = std::min(budget / per_w, (int)MAX_W);
+    if (want_slots > 0) W = std::min(W, std::max(1, (want_slots + lanes - 1) / lanes));
+    if (W < 1) { set_error("one frame's messages do not fit in shared memory"); return LDPC_ERR_UNSUPPORTED; }
+    // CTA size: best check-phase lane efficiency, ties to the larger CTA
+    const int items = W * c.m;
+    int best_t = 0; double best_e = -1;
+    for (int t = 128; t <= k.max_threads; t += 32) {
+        int passes = (items + t - 1) / t;
+        double e = double(items) / (double(passes) * t);
+        int vp = (c.n + t - 1) / t;
+        e = 0.8 * e + 0.2 * double(c.n) / (double(vp) * t);
+        if (e >= best_e - 1e-9) { best_e = e; best_t = t; }
+    }
+    if (want_threads > 0) best_t = std::min(k.max_threads, std::max(32, (want_threads / 32) * 32));
+    out.kernel = k; out.W = W; out.threads = best_t;
+    out.smem = W * per_w + (int)sizeof(Ctrl);
+    cudaError_t e = cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, out.smem);
+    if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return LDPC_ERR_CUDA; }
+    return LDPC_OK;
+}
+
+static int upload_tables(ldpc_decoder &d)
+{
+    const ldpc_code &c = d.code;
+    std::vector<uint8_t> cdeg(c.m), vdeg(c.n);
+    for (int i = 0; i < c.m; ++i) cdeg[i] = (uint8_t)c.cdeg[i];
+    for (int v = 0; v < c.n; ++v) vdeg[v] = (uint8_t)c.vdeg[v];
+    std::vector<uint16_t> vedge((size_t)c.dv_max * c.n, 0);
+    for (int v = 0; v < c.n; ++v)
+        for (int j = 0; j < c.vdeg[v]; ++j) {
+            int chk = c.vlist[(size_t)v * c.dv_max + j], slot = c.vslot[(size_t)v * c.dv_max + j];
+            vedge[(size_t)j * c.n + v] = (uint16_t)(slot * c.m + chk);
+        }
+    CUDA_TRY(cudaMalloc(&d.d_cdeg, cdeg.size()));
+    CUDA_TRY(cudaMalloc(&d.d_vdeg, vdeg.size()));
+    CUDA_TRY(cudaMalloc(&d.d_vedge, vedge.size() * 2));
+    CUDA_TRY(cudaMalloc(&d.d_queue, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&d.d_fb_count, sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d.d_fb_total, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(d.d_fb_total, 0, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemcpy(d.d_cdeg, cdeg.data(), cdeg.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.d_vdeg, vdeg.data(), vdeg.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.d_vedge, vedge.data(), vedge.size() * 2, cudaMemcpyHostToDevice));
+    return LDPC_OK;
+}
+
+// ---- fallback plumbing: list the frames the packed kernel flagged (iters == -1) -------------
+__global__ void collect_flagged(const int *iters, long long frames, int *index, int *count, unsigned long long *total)
+{
+    long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (f < frames && iters[f] < 0) {
+        index[atomicAdd(count, 1)] = (int)f;
+        atomicAdd(total, 1ull);
+    }
+}
+
+static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, int llr_bits, long long frames,
+                  int *iters, uint32_t *bits, int *post, int *v2c, const int *index, const int *count,
+                  cudaStream_t st)
+{
+    if (frames <= 0) return LDPC_OK;
+    const ldpc_code &c = d.code;
+    KParams p;
+    p.cdeg = d.d_cdeg; p.vdeg = d.d_vdeg; p.vedge = d.d_vedge;
+    p.n = c.n; p.m = c.m; p.E = c.edges; p.dc_max = c.dc_max; p.dv_max = c.dv_max;
+    p.W = pl.W; p.max_iter = d.cfg.max_iter; p.precheck = d.cfg.precheck;
+    p.llr = llr; p.llr_bits = llr_bits; p.frames = frames;
+    p.iters = iters; p.bits = bits; p.nw32 = (c.n + 31) / 32; p.post = post; p.v2c = v2c;
+    p.queue = d.d_queue + which;
+    p.index = index; p.count = count;
+    const int lanes = which == 0 ? 2 : 1;
+    const long long slots = (long long)pl.W * lanes;
+    int grid = (int)std::min<long long>(d.sm_count, (frames + slots - 1) / slots);
+    CUDA_TRY(cudaMemsetAsync(p.queue, 0, sizeof(unsigned long long), st));
+    pl.kernel.fn<<<grid, pl.threads, pl.smem, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    d.stats.kernel_launches++;
+    d.stats.grid = grid;
+    return LDPC_OK;
+}
+
+static int decode_device(ldpc_decoder &d, const void *llr, int llr_bits, long long frames, int *iters,
+                         uint32_t *bits, int *post, int *v2c, cudaStream_t st)
+{
+    if (llr_bits != 16 && llr_bits != 32) { set_error("llr_bits must be 16 or 32"); return LDPC_ERR_ARG; }
+    if (frames > 0x7fffffffLL) { set_error("more than 2^31-1 frames in one call"); return LDPC_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(d.device));
+    d.stats.frames += (uint64_t)frames;
+    if (d.cfg.precision == 32)
+        return launch(d, d.plan32, 1, llr, llr_bits, frames, iters, bits, post, v2c, nullptr, nullptr, st);
+    int rc = launch(d, d.plan16, 0, llr, llr_bits, frames, iters, bits, post, v2c, nullptr, nullptr, st);
+    if (rc != LDPC_OK || d.cfg.precision == 16) return rc;
+    // Exact int32 re-decode of the flagged frames, in place and without a host round trip: the
+    // second launch reads the frame list and its length from device memory.
+    if (d.fb_cap < (size_t)frames) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(d.d_fb_index);
+        d.d_fb_index = nullptr; d.fb_cap = 0;
+        CUDA_TRY(cudaMalloc(&d.d_fb_index, (size_t)frames * sizeof(int)));
+        d.fb_cap = (size_t)frames;
+    }
+    CUDA_TRY(cudaMemsetAsync(d.d_fb_count, 0, sizeof(int), st));
+    collect_flagged<<<(unsigned)((frames + 255) / 256), 256, 0, st>>>(iters, frames, d.d_fb_index, d.d_fb_count, d.d_fb_total);
+    CUDA_TRY(cudaGetLastError());
+    d.stats.kernel_launches++;
+    return launch(d, d.plan32, 1, llr, llr_bits, frames, iters, bits, post, v2c, d.d_fb_index, d.d_fb_count, st);
+}
+
+static void free_staging(ldpc_decoder &d)
+{
+    cudaFree(d.d_llr); cudaFree(d.d_iters); cudaFree(d.d_bits); cudaFree(d.d_post); cudaFree(d.d_v2c);
+    d.d_llr = nullptr; d.d_iters = nullptr; d.d_bits = nullptr; d.d_post = nullptr; d.d_v2c = nullptr;
+    d.cap_frames = 0; d.cap_post = d.cap_v2c = false;
+}
+
+static int ensure_staging(ldpc_decoder &d, size_t frames, bool post, bool v2c)
+{
+    if (d.cap_frames >= frames && (!post || d.cap_post) && (!v2c || d.cap_v2c)) return LDPC_OK;
+    const ldpc_code &c = d.code;
+    size_t cap = std::max(frames, d.cap_frames);
+    post |= d.cap_post; v2c |= d.cap_v2c;
+    free_staging(d);
+    CUDA_TRY(cudaMalloc(&d.d_llr, cap * c.n * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d.d_iters, cap * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d.d_bits, cap * ((c.n + 31) / 32) * sizeof(uint32_t)));
+    if (post) CUDA_TRY(cudaMalloc(&d.d_post, cap * c.n * sizeof(int)));
+    if (v2c) CUDA_TRY(cudaMalloc(&d.d_v2c, cap * (size_t)c.dc_max * c.m * sizeof(int)));
+    d.cap_frames = cap; d.cap_post = post; d.cap_v2c = v2c;
+    return LDPC_OK;
+}
+
+}  // namespace ldpc
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char *ldpc_strerror(int status)
+{
+    switch (status) {
+    case LDPC_OK: return "ok";
+    case LDPC_ERR_IO: return "cannot open or read file";
+    case LDPC_ERR_FORMAT: return "malformed parity-check description";
+    case LDPC_ERR_ARG: return "invalid argument";
+    case LDPC_ERR_CUDA: return "CUDA runtime error";
+    case LDPC_ERR_UNSUPPORTED: return "code does not fit the decode kernels";
+    case LDPC_ERR_NOMEM: return "out of memory";
+    case LDPC_ERR_NO_DEVICE: return "no CUDA device (this engine has no CPU path)";
+    default: return "unknown status";
+    }
+}
+
+const char *ldpc_last_error(void) { return ldpc::last_error(); }
+
+static ldpc_code *finish_code(int st, ldpc_code *c, int *err)
+{
+    if (err) *err = st;
+    if (st != LDPC_OK) { delete c; return nullptr; }
+    return c;
+}
+
+ldpc_code *ldpc_code_load(const char *path, int format, int *err)
+{
+    ldpc_code *c = new ldpc_code;
+    return finish_code(ldpc::load_file(path, format, *c), c, err);
+}
+
+ldpc_code *ldpc_code_from_checks(int n, int m, const int *cdeg, const int *clist, int cstride, int *err)
+{
+    ldpc_code *c = new ldpc_code;
+    return finish_code(ldpc::build_from_checks(n, m, cdeg, clist, cstride, *c), c, err);
+}
+
+ldpc_code *ldpc_code_array(int p, int nrows, const int *row_mult, int ncols, const int *col_sel, int backward, int *err)
+{
+    ldpc_code *c = new ldpc_code;
+    return finish_code(ldpc::build_array(p, nrows, row_mult, ncols, col_sel, backward, *c), c, err);
+}
+
+void ldpc_code_free(ldpc_code *code) { delete code; }
+
+int ldpc_code_dims(const ldpc_code *c, int *n, int *m, int *edges, int *dc_max, int *dv_max)
+{
+    if (!c) return LDPC_ERR_ARG;
+    if (n) *n = c->n;
+    if (m) *m = c->m;
+    if (edges) *edges = c->edges;
+    if (dc_max) *dc_max = c->dc_max;
+    if (dv_max) *dv_max = c->dv_max;
+    return LDPC_OK;
+}
+
+int ldpc_code_tables(const ldpc_code *c, int *vdeg, int *cdeg, int *vlist, int *clist)
+{
+    if (!c) return LDPC_ERR_ARG;
+    if (vdeg) std::copy(c->vdeg.begin(), c->vdeg.end(), vdeg);
+    if (cdeg) std::copy(c->cdeg.begin(), c->cdeg.end(), cdeg);
+    if (vlist) std::copy(c->vlist.begin(), c->vlist.end(), vlist);
+    if (clist) std::copy(c->clist.begin(), c->clist.end(), clist);
+    return LDPC_OK;
+}
+
+double ldpc_code_rate(const ldpc_code *c) { return c ? c->rate : 0.0; }
+
+int ldpc_code_save(const ldpc_code *c, const char *path)
+{
+    if (!c || !path) return LDPC_ERR_ARG;
+    return ldpc::save_format_a(*c, path);
+}
+
+void ldpc_decoder_cfg_default(ldpc_decoder_cfg *cfg)
+{
+    if (!cfg) return;
+    cfg->max_iter = 30;  // MAX_ITER, ArrayLDPCMacro.h:17
+    cfg->precheck = 0;
+    cfg->device = 0;
+    cfg->precision = 0;
+    cfg->threads = 0;
+    cfg->frames_per_cta = 0;
+}
+
+int ldpc_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { ldpc::set_error(cudaGetErrorString(e)); cudaGetLastError(); return LDPC_ERR_NO_DEVICE; }
+    return n;
+}
+
+ldpc_decoder *ldpc_decoder_create(const ldpc_code *code, const ldpc_decoder_cfg *cfg_in, int *err)
+{
+    int st = LDPC_OK;
+    ldpc_decoder *d = nullptr;
+    ldpc_decoder_cfg cfg;
+    ldpc_decoder_cfg_default(&cfg);
+    if (cfg_in) cfg = *cfg_in;
+    auto fail = [&](int s) { if (err) *err = s; if (d) ldpc_decoder_destroy(d); return (ldpc_decoder *)nullptr; };
+    if (!code) { ldpc::set_error("NULL code"); return fail(LDPC_ERR_ARG); }
+    if (cfg.max_iter < 1 || (cfg.precision != 0 && cfg.precision != 16 && cfg.precision != 32)) {
+        ldpc::set_error("max_iter < 1 or unknown precision"); return fail(LDPC_ERR_ARG);
+    }
+    int ndev = ldpc_device_count();
+    if (ndev <= 0) { if (ndev == 0) ldpc::set_error("no CUDA device visible"); return fail(LDPC_ERR_NO_DEVICE); }
+    if (cfg.device < 0 || cfg.device >= ndev) { ldpc::set_error("device ordinal out of range"); return fail(LDPC_ERR_ARG); }
+    d = new ldpc_decoder;
+    d->code = *code; d->cfg = cfg; d->device = cfg.device;
+    std::memset(&d->stats, 0, sizeof d->stats);
+    cudaError_t e = cudaSetDevice(cfg.device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, cfg.device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg.device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { ldpc::set_error(cudaGetErrorString(e)); return fail(LDPC_ERR_CUDA); }
+    if ((st = ldpc::upload_tables(*d)) != LDPC_OK) return fail(st);
+    if ((st = ldpc::make_plan(*d, 2, ldpc::pick_kernel<ldpc::Packed16>(d->code), cfg.threads, cfg.frames_per_cta, d->plan16)) != LDPC_OK) return fail(st);
+    if ((st = ldpc::make_plan(*d, 1, ldpc::pick_kernel<ldpc::Scalar32>(d->code), cfg.threads, cfg.frames_per_cta, d->plan32)) != LDPC_OK) return fail(st);
+    d->stats.threads = d->plan16.threads; d->stats.threads32 = d->plan32.threads;
+    d->stats.frames_per_cta = d->plan16.W * 2; d->stats.frames_per_cta32 = d->plan32.W;
+    d->stats.smem_bytes = d->plan16.smem; d->stats.smem_bytes32 = d->plan32.smem;
+    if (err) *err = LDPC_OK;
+    return d;
+}
+
+void ldpc_decoder_destroy(ldpc_decoder *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    ldpc::free_staging(*d);
+    cudaFree(d->d_cdeg); cudaFree(d->d_vdeg); cudaFree(d->d_vedge); cudaFree(d->d_queue);
+    cudaFree(d->d_fb_index); cudaFree(d->d_fb_count); cudaFree(d->d_fb_total);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+int ldpc_decode_batch_device(ldpc_decoder *d, const void *d_llr, int llr_bits, size_t frames, int32_t *d_iters,
+                             uint32_t *d_bits, int32_t *d_post, int32_t *d_v2c, void *stream)
+{
+    if (!d || !d_llr || !d_iters) { ldpc::set_error("NULL decoder / llr / iters"); return LDPC_ERR_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    return ldpc::decode_device(*d, d_llr, llr_bits, (long long)frames, d_iters, d_bits, d_post, d_v2c, st);
+}
+
+int ldpc_decode_batch(ldpc_decoder *d, const int32_t *llr, size_t frames, int32_t *iters, uint32_t *bits,
+                      int32_t *post, int32_t *v2c)
+{
+    if (!d || !llr || !iters) { ldpc::set_error("NULL decoder / llr / iters"); return LDPC_ERR_ARG; }
+    if (frames == 0) return LDPC_OK;
+    CUDA_TRY(cudaSetDevice(d->device));
+    int rc = ldpc::ensure_staging(*d, frames, post != nullptr, v2c != nullptr);
+    if (rc != LDPC_OK) return rc;
+    const ldpc_code &c = d->code;
+    const size_t nw32 = (c.n + 31) / 32, vsz = (size_t)c.dc_max * c.m;
+    cudaStream_t st = d->stream;
+    CUDA_TRY(cudaMemcpyAsync(d->d_llr, llr, frames * c.n * sizeof(int), cudaMemcpyHostToDevice, st));
+    rc = ldpc::decode_device(*d, d->d_llr, 32, (long long)frames, d->d_iters, bits ? d->d_bits : nullptr,
+                             post ? d->d_post : nullptr, v2c ? d->d_v2c : nullptr, st);
+    if (rc != LDPC_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(iters, d->d_iters, frames * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (bits) CUDA_TRY(cudaMemcpyAsync(bits, d->d_bits, frames * nw32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (post) CUDA_TRY(cudaMemcpyAsync(post, d->d_post, frames * c.n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (v2c) CUDA_TRY(cudaMemcpyAsync(v2c, d->d_v2c, frames * vsz * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return LDPC_OK;
+}
+
+int ldpc_decoder_sync(ldpc_decoder *d)
+{
+    if (!d) return LDPC_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(d->device));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    return LDPC_OK;
+}
+
+int ldpc_decoder_get_stats(const ldpc_decoder *d, ldpc_decoder_stats *out)
+{
+    if (!d || !out) return LDPC_ERR_ARG;
+    *out = d->stats;
+    if (d->d_fb_total) {  // blocking read of the device-side counter
+        unsigned long long total = 0;
+        CUDA_TRY(cudaSetDevice(d->device));
+        CUDA_TRY(cudaMemcpy(&total, d->d_fb_total, sizeof total, cudaMemcpyDeviceToHost));
+        out->fallback_frames = total;
+    }
+    return LDPC_OK;
+}
+
+}  // extern "C"

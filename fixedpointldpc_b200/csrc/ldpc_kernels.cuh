@@ -1,0 +1,456 @@
+// ldpc_kernels.cuh -- sm_100a decode kernels of the fixed-point LDPC engine.
+//
+// One persistent CTA per SM keeps W "word sets" resident in shared memory for the whole life
+// of the frames decoded in them: E edge messages + n channel values, one 32-bit word each.
+// A word holds one frame (Scalar32: exact int32 arithmetic) or two frames (Packed16: int16x2
+// lanes, 13-bit magnitude guard).  Every lane of every word set is an independent frame slot
+// with its own iteration counter; a slot that finishes is refilled from a global queue, so
+// early termination never idles the other slots.
+//
+// Per trip of the main loop (== one flooding iteration of ArrayLDPC_Decoder.cpp:63-168 for
+// every resident frame):
+//   variable phase  (ArrayLDPC_Decoder.cpp:121-156)  thread per variable, gather over the
+//                   static edge-address table; also writes the hard decision of the
+//                   posterior into a spare bit of every outgoing message
+//   syndrome pass   (ArrayLDPC_Decoder.cpp:296-333)  thread per check XORs those spare bits
+//   bookkeeping     early termination / max_iter / pre-check (:164-167, :443-450), output,
+//                   slot refill
+//   check phase     (ArrayLDPC_Decoder.cpp:66-118)   thread per check, forward chain kept in
+//                   registers, backward chain + combine fused with the write-back
+//
+// Message words in shared memory
+//   v2c (variable -> check): sign | hd | magnitude   (Scalar32: bit31 | bit30 | 30 bits,
+//                                                     Packed16 lane: bit15 | bit14 | 14 bits)
+//   c2v (check -> variable): two's complement of -c2v (negated so the variable phase only adds)
+// The pairwise operator sxor (ArrayLDPC_Decoder.cpp:677-694) is evaluated on magnitudes only;
+// the sign of every outgoing message is the XOR of the incoming sign bits, which is exact
+// because a zero magnitude absorbs (sxor(0,y) == 0) and sgn(0) only matters when the result is 0.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ldpc {
+
+struct KParams {
+    // code
+    const uint8_t *cdeg;    // [m]
+    const uint8_t *vdeg;    // [n]
+    const uint16_t *vedge;  // [dv_max][n]  word index (slot*m + check) of edge j of variable v
+    int n, m, E, dc_max, dv_max;
+    // schedule
+    int W;         // word sets per CTA
+    int max_iter;  // MAX_ITER
+    int precheck;  // decode_fixpoint's hardDecision pre-check
+    // io
+    const void *llr;  // [frames][n] int32 or int16
+    int llr_bits;
+    long long frames;
+    int *iters;      // [frames]
+    uint32_t *bits;  // [frames][nw32] or NULL
+    int nw32;
+    int *post;  // [frames][n] or NULL
+    int *v2c;   // [frames][dc_max][m] or NULL
+    unsigned long long *queue;  // next frame index
+    // optional indirection (exact re-decode of the frames the packed kernel flagged): queue
+    // position q decodes frame index[q], and the number of positions is *count
+    const int *index;
+    const int *count;
+};
+
+// ------------------------------------------------------------------------------------------
+// lane traits
+// ------------------------------------------------------------------------------------------
+
+// One frame per word, exact while every value stays below 2^30 in magnitude.
+struct Scalar32 {
+    static constexpr int LANES = 1;
+    static constexpr uint32_t MAG = 0x3fffffffu, SIGN = 0x80000000u, HD = 0x40000000u;
+    static constexpr uint32_t ALL = 0xffffffffu;
+
+    __device__ static __forceinline__ uint32_t lane_mask(int) { return 0xffffffffu; }
+
+    // magnitude part of sxor: min + max(0,10-(sum&255)>>2) - max(0,10-(diff&255)>>2)
+    //                       = min + min(10,(diff&255)>>2) - min(10,(sum&255)>>2)
+    __device__ static __forceinline__ uint32_t g(uint32_t a, uint32_t b)
+    {
+        uint32_t mn = min(a, b);
+        uint32_t s = a + b;
+        uint32_t d = s - 2u * mn;
+        uint32_t pk = __byte_perm(s, d, 0x5410);          // [d.lo16 | s.lo16]
+        uint32_t q = (pk >> 2) & 0x003f003fu;             // ((x & 255) >> 2) per half
+        uint32_t u = __vminu2(q, 0x000a000au);
+        return (uint32_t)__dp2a_lo((int)u, 0x000001ff, (int)mn);  // mn - u(sum) + u(diff)
+    }
+    // word written by the check phase: -c2v where c2v = (sign bit of nsign set) ? -o : +o
+    __device__ static __forceinline__ uint32_t neg_c2v(uint32_t o, uint32_t nsign)
+    {
+        uint32_t mneg = ~(uint32_t)((int)nsign >> 31);  // all ones where c2v > 0 -> store -o
+        return (o ^ mneg) - mneg;
+    }
+    __device__ static __forceinline__ uint32_t fail_bits(uint32_t acc) { return (acc >> 30) & 1u; }
+
+    struct Acc { int v; };
+    __device__ static __forceinline__ Acc acc_init(uint32_t llr) { return Acc{(int)llr}; }
+    __device__ static __forceinline__ void acc_sub(Acc &a, uint32_t nc) { a.v -= (int)nc; }
+    // posterior word + hard-decision bits in message position; no guard needed
+    __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd, uint32_t &)
+    {
+        hd = a.v <= 0 ? HD : 0u;
+        return (uint32_t)a.v;
+    }
+    __device__ static __forceinline__ uint32_t v2c_word(uint32_t post, uint32_t nc, uint32_t hd, uint32_t &)
+    {
+        int v = (int)post + (int)nc;
+        return (uint32_t)abs(v) | ((uint32_t)v & SIGN) | hd;
+    }
+    __device__ static __forceinline__ uint32_t guard_lanes(uint32_t) { return 0u; }
+    __device__ static __forceinline__ int lane_value(uint32_t w, int) { return (int)w; }
+    __device__ static __forceinline__ int v2c_value(uint32_t w, int)
+    {
+        int mag = (int)(w & MAG);
+        return (w & SIGN) ? -mag : mag;
+    }
+    __device__ static __forceinline__ uint32_t hd_bit(uint32_t w, int) { return (w >> 30) & 1u; }
+    __device__ static __forceinline__ uint32_t set_lane(uint32_t, int, int val, bool &bad)
+    {
+        bad = false;
+        return (uint32_t)val;
+    }
+};
+
+// Two frames per word (int16x2).  Exact as long as every |LLR|, |posterior| and |message| stays
+// below 2^13; a lane that leaves that range is flagged and its frame is re-decoded by the
+// Scalar32 kernel (there is no saturation in the reference).
+struct Packed16 {
+    static constexpr int LANES = 2;
+    static constexpr uint32_t MAG = 0x1fff1fffu, SIGN = 0x80008000u, HD = 0x40004000u;
+    static constexpr uint32_t GUARD = 0x60006000u;  // magnitude bits 13,14 of the un-flagged word
+    static constexpr uint32_t ALL = 0xffffffffu;
+    static constexpr int LIMIT = 1 << 13;
+
+    __device__ static __forceinline__ uint32_t lane_mask(int lane) { return lane ? 0xffff0000u : 0x0000ffffu; }
+
+    __device__ static __forceinline__ uint32_t g(uint32_t a, uint32_t b)
+    {
+        uint32_t mn = __vminu2(a, b);
+        uint32_t s = a + b;                      // lanes < 2^15: no carry across
+        uint32_t d = s - 2u * mn;                // |a-b| per lane, no borrow
+        uint32_t us = __vminu2(s & 0x00fc00fcu, 0x00280028u);  // 4*min(10,(s&255)>>2)
+        uint32_t ud = __vminu2(d & 0x00fc00fcu, 0x00280028u);
+        uint32_t x = 4u * mn + ud - us;          // 4*(mn + u(diff) - u(sum)), lanes < 2^16
+        return x >> 2;                           // low two bits of every lane are zero
+    }
+    __device__ static __forceinline__ uint32_t neg_c2v(uint32_t o, uint32_t nsign)
+    {
+        uint32_t mneg = __byte_perm(~nsign, 0, 0xbb99);  // 0xffff in lanes where c2v > 0
+        return __vadd2(o, mneg) ^ mneg;                  // ~(o-1) == -o in those lanes
+    }
+    __device__ static __forceinline__ uint32_t fail_bits(uint32_t acc)
+    {
+        return ((acc >> 14) & 1u) | ((acc >> 29) & 2u);
+    }
+
+    struct Acc { int lo, hi; };
+    __device__ static __forceinline__ Acc acc_init(uint32_t llr)
+    {
+        return Acc{__dp2a_lo((int)llr, 0x00000001, 0), __dp2a_lo((int)llr, 0x00000100, 0)};
+    }
+    __device__ static __forceinline__ void acc_sub(Acc &a, uint32_t nc)
+    {
+        a.lo = __dp2a_lo((int)nc, 0x000000ff, a.lo);  // -= (int16) low lane
+        a.hi = __dp2a_lo((int)nc, 0x0000ff00, a.hi);  // -= (int16) high lane
+    }
+    __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd, uint32_t &guard)
+    {
+        hd = (a.lo <= 0 ? 0x00004000u : 0u) | (a.hi <= 0 ? 0x40000000u : 0u);
+        // posterior must fit the lane with headroom for post + (-c2v)
+        guard |= ((uint32_t)(a.lo + LIMIT) >= 2u * LIMIT ? 0x00002000u : 0u) |
+                 ((uint32_t)(a.hi + LIMIT) >= 2u * LIMIT ? 0x20000000u : 0u);
+        return __byte_perm((uint32_t)a.lo, (uint32_t)a.hi, 0x5410);
+    }
+    __device__ static __forceinline__ uint32_t v2c_word(uint32_t post, uint32_t nc, uint32_t hd, uint32_t &guard)
+    {
+        uint32_t v = __vadd2(post, nc);
+        uint32_t m = __byte_perm(v, 0, 0xbb99);          // 0xffff in negative lanes
+        uint32_t t = __vadd2(v, m);                      // v-1 there
+        uint32_t ms = t ^ (m & 0x7fff7fffu);             // sign | |v|
+        guard |= ms;
+        return ms | hd;
+    }
+    __device__ static __forceinline__ uint32_t guard_lanes(uint32_t guard)
+    {
+        return ((guard & 0x00006000u) ? 1u : 0u) | ((guard & 0x60000000u) ? 2u : 0u);
+    }
+    __device__ static __forceinline__ int lane_value(uint32_t w, int lane)
+    {
+        return (int)(int16_t)(lane ? (w >> 16) : (w & 0xffffu));
+    }
+    __device__ static __forceinline__ int v2c_value(uint32_t w, int lane)
+    {
+        uint32_t h = lane ? (w >> 16) : (w & 0xffffu);
+        int mag = (int)(h & 0x3fffu);
+        return (h & 0x8000u) ? -mag : mag;
+    }
+    __device__ static __forceinline__ uint32_t hd_bit(uint32_t w, int lane) { return (w >> (lane ? 30 : 14)) & 1u; }
+    __device__ static __forceinline__ uint32_t set_lane(uint32_t old, int lane, int val, bool &bad)
+    {
+        bad = (uint32_t)(val + LIMIT) >= 2u * LIMIT;
+        uint32_t h = (uint32_t)val & 0xffffu;
+        return lane ? ((old & 0x0000ffffu) | (h << 16)) : ((old & 0xffff0000u) | h);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// control block in shared memory (after the message and channel words)
+// ------------------------------------------------------------------------------------------
+constexpr int MAX_W = 16;         // word sets per CTA
+constexpr int MAX_SLOTS = 2 * MAX_W;
+
+struct Ctrl {
+    uint32_t fail[MAX_W];   // per word set: lanes with at least one unsatisfied check
+    uint32_t keep[MAX_W];   // per word set: lane masks whose c2v take part in the variable phase
+    uint32_t gflag[MAX_W];  // per word set: lanes that left the guard range (Packed16)
+    int fid[MAX_SLOTS];     // frame index decoded in the slot, -1 = idle
+    int it[MAX_SLOTS];      // iterations completed by that frame
+};
+
+template <int DC> struct LaunchShape {
+    static constexpr int MAX_THREADS = DC <= 32 ? 1024 : (DC <= 48 ? 768 : 512);
+};
+
+// ------------------------------------------------------------------------------------------
+// check phase for one check node, messages e[k*m], k < d
+// ------------------------------------------------------------------------------------------
+template <class T, int DC, bool REG>
+__device__ __forceinline__ void check_node(uint32_t *e, int m, int d)
+{
+    uint32_t fwd[DC - 1];
+    const uint32_t w0 = e[0];
+    uint32_t acc = w0;
+    fwd[0] = w0 & T::MAG;
+    uint32_t last = fwd[0];  // ends as Forward[d-2] without a runtime-indexed read of fwd[]
+#pragma unroll
+    for (int k = 1; k < DC; ++k) {
+        if (REG || k < d) {
+            uint32_t w = e[k * m];
+            acc ^= w;
+            if (k < DC - 1 && (REG || k < d - 1)) {
+                fwd[k] = T::g(fwd[k - 1], w & T::MAG);
+                last = fwd[k];
+            }
+        }
+    }
+    // bit 31/15 of acc: parity of the incoming signs.  Outgoing sign of slot k = acc ^ sign_k.
+    uint32_t bwd = 0;
+#pragma unroll
+    for (int k = DC - 1; k >= 1; --k) {
+        if (REG || k < d) {
+            uint32_t w = e[k * m];
+            uint32_t mag = w & T::MAG;
+            uint32_t o;
+            if (REG ? (k == DC - 1) : (k == d - 1)) {
+                o = last;  // c2v[d-1] = Forward[d-2]
+                bwd = mag;
+            } else {
+                o = T::g(fwd[k - 1], bwd);  // c2v[k] = sxor(Forward[k-1], Backward[k+1])
+                bwd = T::g(bwd, mag);       // Backward[k]
+            }
+            e[k * m] = T::neg_c2v(o, acc ^ w);
+        }
+    }
+    e[0] = T::neg_c2v(bwd, acc ^ w0);  // c2v[0] = Backward[1]
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <class T, int DC, bool REG, int DV>
+__global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel(const KParams p)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
+    const int n = p.n, m = p.m, E = p.E, W = p.W;
+    uint32_t *edge = smem;                // [W][E]
+    uint32_t *llr = edge + (size_t)W * E;  // [W][n]
+    Ctrl *ctrl = reinterpret_cast<Ctrl *>(llr + (size_t)W * n);
+    const int nslots = W * T::LANES;
+    const long long frames = p.count ? (long long)*p.count : p.frames;
+
+    for (int i = tid; i < W * (E + n); i += nthreads) smem[i] = 0u;
+    if (tid < MAX_W) { ctrl->fail[tid] = 0u; ctrl->keep[tid] = 0u; ctrl->gflag[tid] = 0u; }
+    if (tid < MAX_SLOTS) { ctrl->fid[tid] = -1; ctrl->it[tid] = 0; }
+    __syncthreads();
+
+    uint32_t fin = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);  // slots to (re)fill
+    bool first = true;
+    const int items = W * m;
+
+    for (;;) {
+        // ---------------------------------------------------------------- finish + refill
+        if (fin) {
+            if (!first) {
+                // results of the frames that stop now (smem state == after their last variable phase)
+                for (int s = 0; s < nslots; ++s) {
+                    if (!((fin >> s) & 1u)) continue;
+                    const int w = s / T::LANES, lane = s % T::LANES;
+                    const int f = ctrl->fid[s];
+                    const bool overflow = (ctrl->gflag[w] >> lane) & 1u;
+                    if (tid == 0) p.iters[f] = overflow ? -1 : ctrl->it[s];
+                    const uint32_t *ew = edge + (size_t)w * E;
+                    if (p.bits) {
+                        for (int v0 = 0; v0 < n; v0 += nthreads) {
+                            const int v = v0 + tid;
+                            uint32_t b = 0;
+                            if (v < n) {
+                                if (p.vdeg[v]) b = T::hd_bit(ew[p.vedge[v]], lane);
+                                else b = T::lane_value(llr[(size_t)w * n + v], lane) <= 0;
+                            }
+                            const uint32_t word = __ballot_sync(0xffffffffu, b);
+                            if (lane_id == 0 && v < n) p.bits[(size_t)f * p.nw32 + (v >> 5)] = word;
+                        }
+                    }
+                    if (p.v2c) {
+                        int *out = p.v2c + (size_t)f * p.dc_max * m;
+                        for (int i = tid; i < p.dc_max * m; i += nthreads) {
+                            const int k = i / m, c = i - k * m;
+                            out[i] = k < (REG ? DC : (int)p.cdeg[c]) ? T::v2c_value(ew[i], lane) : 0;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                for (int s = 0; s < nslots; ++s) {
+                    if (!((fin >> s) & 1u)) continue;
+                    const int w = s / T::LANES, lane = s % T::LANES;
+                    const unsigned long long f = atomicAdd(p.queue, 1ull);
+                    ctrl->fid[s] = f < (unsigned long long)frames ? (p.index ? p.index[f] : (int)f) : -1;
+                    ctrl->it[s] = 0;
+                    ctrl->keep[w] &= ~T::lane_mask(lane);  // fresh: the next variable phase sees c2v == 0
+                    ctrl->gflag[w] &= ~(1u << lane);
+                }
+            }
+            __syncthreads();
+            for (int s = 0; s < nslots; ++s) {
+                if (!((fin >> s) & 1u)) continue;
+                const int w = s / T::LANES, lane = s % T::LANES;
+                const int f = ctrl->fid[s];
+                bool any_bad = false;
+                for (int v = tid; v < n; v += nthreads) {
+                    int val = 0;
+                    if (f >= 0)
+                        val = p.llr_bits == 16 ? (int)reinterpret_cast<const int16_t *>(p.llr)[(size_t)f * n + v]
+                                               : reinterpret_cast<const int *>(p.llr)[(size_t)f * n + v];
+                    bool bad;
+                    uint32_t *dst = &llr[(size_t)w * n + v];
+                    *dst = T::set_lane(*dst, lane, val, bad);
+                    any_bad |= bad;
+                }
+                if (any_bad) atomicOr(&ctrl->gflag[w], 1u << lane);
+            }
+            __syncthreads();
+            int active = 0;
+            for (int s = 0; s < nslots; ++s) active += ctrl->fid[s] >= 0;
+            if (active == 0) break;
+            first = false;
+        }
+
+        // ---------------------------------------------------------------- check phase
+        // (a freshly refilled lane runs it on stale words; its c2v are masked off below)
+        for (int i = tid; i < items; i += nthreads) {
+            const int w = i / m, c = i - w * m;
+            check_node<T, DC, REG>(edge + (size_t)w * E + c, m, REG ? DC : (int)p.cdeg[c]);
+        }
+        __syncthreads();
+
+        // ---------------------------------------------------------------- variable phase
+        for (int v = tid; v < n; v += nthreads) {
+            const int dv = p.vdeg[v];
+            int addr[DV];
+#pragma unroll
+            for (int j = 0; j < DV; ++j) addr[j] = j < dv ? (int)p.vedge[(size_t)j * n + v] : 0;
+            for (int w = 0; w < W; ++w) {
+                uint32_t *ew = edge + (size_t)w * E;
+                const uint32_t keep = ctrl->keep[w];
+                typename T::Acc acc = T::acc_init(llr[(size_t)w * n + v]);
+                uint32_t x[DV];
+#pragma unroll
+                for (int j = 0; j < DV; ++j)
+                    if (j < dv) { x[j] = ew[addr[j]] & keep; T::acc_sub(acc, x[j]); }
+                uint32_t hd, guard = 0;
+                const uint32_t pw = T::post_word(acc, hd, guard);
+#pragma unroll
+                for (int j = 0; j < DV; ++j)
+                    if (j < dv) ew[addr[j]] = T::v2c_word(pw, x[j], hd, guard);
+                if (T::LANES > 1) {
+                    const uint32_t g = T::guard_lanes(guard);
+                    if (g) atomicOr(&ctrl->gflag[w], g);
+                }
+                if (p.post) {
+#pragma unroll
+                    for (int lane = 0; lane < T::LANES; ++lane) {
+                        const int f = ctrl->fid[w * T::LANES + lane];
+                        if (f >= 0) p.post[(size_t)f * n + v] = T::lane_value(pw, lane);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---------------------------------------------------------------- syndrome pass
+        for (int i0 = tid - lane_id; i0 < items; i0 += nthreads) {
+            const int i = i0 + lane_id;
+            const bool valid = i < items;
+            int w = 0;
+            uint32_t fb = 0;
+            if (valid) {
+                w = i / m;
+                const int c = i - w * m;
+                const uint32_t *e = edge + (size_t)w * E + c;
+                const int d = REG ? DC : (int)p.cdeg[c];
+                uint32_t acc = 0;
+#pragma unroll
+                for (int k = 0; k < DC; ++k)
+                    if (REG || k < d) acc ^= e[k * m];
+                fb = T::fail_bits(acc);
+            }
+            const int w0 = __shfl_sync(0xffffffffu, w, 0);
+            // a warp covers at most two word sets when m >= 32; anything else goes the slow way
+            const uint32_t r0 = __reduce_or_sync(0xffffffffu, (valid && w == w0) ? fb : 0u);
+            const uint32_t r1 = __reduce_or_sync(0xffffffffu, (valid && w == w0 + 1) ? fb : 0u);
+            if (lane_id == 0) {
+                if (r0) atomicOr(&ctrl->fail[w0], r0);
+                if (r1) atomicOr(&ctrl->fail[w0 + 1], r1);
+            }
+            if (valid && w > w0 + 1 && fb) atomicOr(&ctrl->fail[w], fb);
+        }
+        __syncthreads();
+
+        // ---------------------------------------------------------------- bookkeeping
+        // Every thread derives the same stop mask; thread 0 then commits the counters.
+        fin = 0;
+        for (int s = 0; s < nslots; ++s) {
+            const int w = s / T::LANES, lane = s % T::LANES;
+            const bool fresh = (ctrl->keep[w] & T::lane_mask(lane)) == 0u;
+            const int it = ctrl->it[s] + (fresh ? 0 : 1);
+            const bool pass = !((ctrl->fail[w] >> lane) & 1u);
+            const bool over = (ctrl->gflag[w] >> lane) & 1u;
+            const bool stop = it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over;
+            if (ctrl->fid[s] >= 0 && stop) fin |= 1u << s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int s = 0; s < nslots; ++s) {
+                if (ctrl->fid[s] < 0) continue;
+                const bool fresh = (ctrl->keep[s / T::LANES] & T::lane_mask(s % T::LANES)) == 0u;
+                ctrl->it[s] += fresh ? 0 : 1;
+            }
+            for (int s = 0; s < nslots; ++s)
+                if (ctrl->fid[s] >= 0) ctrl->keep[s / T::LANES] |= T::lane_mask(s % T::LANES);
+            for (int w = 0; w < W; ++w) ctrl->fail[w] = 0u;
+        }
+        if (fin) __syncthreads();  // the finish code reads what thread 0 just wrote
+    }
+}
+
+}  // namespace ldpc

@@ -1,0 +1,146 @@
+/*
+ * ldpc_capi.h -- C ABI of the B200 fixed-point LDPC decode engine (libldpc_b200.so).
+ *
+ * This is the drop-in boundary for the reference's decode path: plain pointers and sizes,
+ * no C++/torch types, no exceptions.  Every entry point names the reference interface it
+ * replaces (file:line in tyc85/FixedPointLDPC).  The C++ facade in ArrayLDPCMacro.h /
+ * PerfTest.h (same directory) re-creates the reference's class and driver names on top of
+ * these calls; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - all functions returning int return LDPC_OK (0) or a negative ldpc_status;
+ *     constructors return NULL and store the status in *err (err may be NULL);
+ *   - a decoder handle is bound to one CUDA device and one stream and must be used from one
+ *     host thread at a time (the reference is not re-entrant at all:
+ *     ArrayLDPC_Decoder.cpp:21-37, 430-440);
+ *   - there is NO CPU fallback: without a CUDA device every decoder call fails with
+ *     LDPC_ERR_NO_DEVICE.
+ */
+#ifndef LDPC_CAPI_H
+#define LDPC_CAPI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ldpc_code ldpc_code;       /* parity-check tables (host)           */
+typedef struct ldpc_gen ldpc_gen;         /* generator equations, Format B (host) */
+typedef struct ldpc_decoder ldpc_decoder; /* device-resident decode engine        */
+
+typedef enum {
+    LDPC_OK = 0,
+    LDPC_ERR_IO = -1,          /* file cannot be opened / short read                      */
+    LDPC_ERR_FORMAT = -2,      /* file parsed but inconsistent (vlist <-> clist, ranges)  */
+    LDPC_ERR_ARG = -3,         /* NULL / out-of-range argument                            */
+    LDPC_ERR_CUDA = -4,        /* CUDA runtime error, see ldpc_last_error()               */
+    LDPC_ERR_UNSUPPORTED = -5, /* code does not fit the kernels (degree / smem limits)    */
+    LDPC_ERR_NOMEM = -6,
+    LDPC_ERR_NO_DEVICE = -7    /* no CUDA device: the engine has no CPU path              */
+} ldpc_status;
+
+/* On-disk H formats. */
+enum {
+    LDPC_FMT_AUTO = 0,
+    LDPC_FMT_A = 1, /* zero-based alist-like, what FP_Decoder::ReadH parses              */
+    LDPC_FMT_C = 3  /* legacy one-based check lists (H2212_316_array_cut79.txt)          */
+};
+
+const char *ldpc_strerror(int status);
+/* Text of the most recent failure on this thread (CUDA error string, offending token, ...). */
+const char *ldpc_last_error(void);
+
+/* ------------------------------------------------------------------ code tables (host) */
+
+/* Replaces FP_Decoder::ReadH (ArrayLDPC_Decoder.cpp:642-674), whose file name is hard
+ * coded (:646) and whose reads are unchecked.  Format C has no reader in the reference. */
+ldpc_code *ldpc_code_load(const char *path, int format, int *err);
+
+/* Build from check lists: clist[c*cstride + k], k < cdeg[c], zero-based.  Rows are sorted
+ * ascending (the reference's addr_count slot lookup needs that, ArrayLDPC_Decoder.cpp:121-154). */
+ldpc_code *ldpc_code_from_checks(int n, int m, const int *cdeg, const int *clist, int cstride, int *err);
+
+/* Array-code structure == class ROM (ArrayLDPCMacro.h:42-82): check (i, t) of row group i
+ * touches variable b*p + ((t + sign*row_mult[i]*col_sel[b]) mod p) of every selected column
+ * group b; sign = +1 ("forward", what decode_fixpoint addresses, ArrayLDPC_Decoder.cpp:474-476)
+ * or -1 when backward != 0.  row_mult/col_sel may be NULL for 0..nrows-1 / 0..ncols-1. */
+ldpc_code *ldpc_code_array(int p, int nrows, const int *row_mult, int ncols, const int *col_sel,
+                           int backward, int *err);
+
+void ldpc_code_free(ldpc_code *code);
+
+/* n, m, edges, dc_max, dv_max  (NUM_VAR, NUM_CHK, -, CHK_DEG, VAR_DEG of ArrayLDPCMacro.h:18-24). */
+int ldpc_code_dims(const ldpc_code *code, int *n, int *m, int *edges, int *dc_max, int *dv_max);
+/* Dense copies of the four ReadH tables; short rows are padded with -1.  Any pointer may be NULL. */
+int ldpc_code_tables(const ldpc_code *code, int *vdeg, int *cdeg, int *vlist, int *clist);
+/* Rate reported by ROM::getRate (ArrayLDPCMacro.h:60) for array codes built by ldpc_code_array,
+ * (n - m)/n otherwise. */
+double ldpc_code_rate(const ldpc_code *code);
+/* Writes Format A exactly as codes/alist_from_arraycode.m:28-60 does. */
+int ldpc_code_save(const ldpc_code *code, const char *path);
+
+/* ------------------------------------------------------------------ decoder (device)  */
+
+typedef struct {
+    int max_iter;   /* MAX_ITER, ArrayLDPCMacro.h:17; default 30                                  */
+    int precheck;   /* 1: decode_fixpoint semantics (return 0 when the channel hard decision
+                       already satisfies H, ArrayLDPC_Decoder.cpp:443-450); 0: decode_general_fp */
+    int device;     /* CUDA device ordinal                                                        */
+    int precision;  /* 0 = auto (packed int16x2 kernel + exact int32 re-decode of frames whose
+                       values leave the 13-bit guard range), 32 = int32 kernel only, 16 = packed
+                       only (frames that leave the range report iters = -1)                       */
+    int threads;    /* CTA size override, 0 = auto                                                */
+    int frames_per_cta; /* resident frame slots per CTA override, 0 = auto                        */
+} ldpc_decoder_cfg;
+
+void ldpc_decoder_cfg_default(ldpc_decoder_cfg *cfg);
+
+ldpc_decoder *ldpc_decoder_create(const ldpc_code *code, const ldpc_decoder_cfg *cfg, int *err);
+void ldpc_decoder_destroy(ldpc_decoder *dec);
+
+/* Batched FP_Decoder::decode_general_fp / decode_fixpoint (ArrayLDPC_Decoder.cpp:18-171,
+ * 422-639) on HOST buffers; copies in, decodes on the GPU, copies out, returns when done.
+ *   llr    [frames][n]            int32, the reference's `const int *LLR`
+ *   iters  [frames]               return value of the reference call (0..max_iter)
+ *   bits   [frames][ceil(n/32)]   DecodedCodeword, bit v%32 of word v/32            (or NULL)
+ *   post   [frames][n]            Posteriori_fp                                     (or NULL)
+ *   v2c    [frames][dc_max][m]    EdgeRAM image, slot-major (ArrayLDPCMacro.h:101,162);
+ *                                 slots >= cdeg[c] are written as 0                 (or NULL)
+ * For frames with iters == 0 (pre-check hit) post/v2c hold the channel values; the reference
+ * leaves them stale (quirk Q6). */
+int ldpc_decode_batch(ldpc_decoder *dec, const int32_t *llr, size_t frames, int32_t *iters,
+                      uint32_t *bits, int32_t *post, int32_t *v2c);
+
+/* Same on DEVICE buffers, asynchronous on `stream` (a cudaStream_t, NULL = the decoder's own
+ * stream).  llr_bits = 32 (int32) or 16 (int16) selects the input element type. */
+int ldpc_decode_batch_device(ldpc_decoder *dec, const void *d_llr, int llr_bits, size_t frames,
+                             int32_t *d_iters, uint32_t *d_bits, int32_t *d_post, int32_t *d_v2c,
+                             void *stream);
+
+/* Blocks until everything queued on the decoder's streams has finished. */
+int ldpc_decoder_sync(ldpc_decoder *dec);
+
+typedef struct {
+    uint64_t kernel_launches;  /* decode kernels launched since creation                     */
+    uint64_t frames;           /* frames decoded                                              */
+    uint64_t fallback_frames;  /* frames re-decoded by the int32 kernel (guard range left)    */
+    int threads;               /* CTA size in use (packed / int32)                            */
+    int threads32;
+    int frames_per_cta;        /* resident frame slots per CTA (packed / int32)               */
+    int frames_per_cta32;
+    int grid;                  /* CTAs per launch                                             */
+    int smem_bytes;            /* dynamic shared memory per CTA (packed kernel)               */
+    int smem_bytes32;
+} ldpc_decoder_stats;
+
+int ldpc_decoder_get_stats(const ldpc_decoder *dec, ldpc_decoder_stats *out);
+
+/* Number of CUDA devices visible, or a negative status. */
+int ldpc_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
