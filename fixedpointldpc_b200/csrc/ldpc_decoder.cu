@@ -87,8 +87,8 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
 {
     const ldpc_code &c = d.code;
     if (!k.fn) { set_error("check degree > 64 or variable degree > 32: no kernel instantiation"); return LDPC_ERR_UNSUPPORTED; }
-    if (c.edges > 65535) { set_error("more than 65535 edges"); return LDPC_ERR_UNSUPPORTED; }
-    const int per_w = (c.edges + c.n) * 4;
+    if ((long long)c.dc_max * c.m > 65535) { set_error("dc_max*m exceeds the 16-bit edge address space"); return LDPC_ERR_UNSUPPORTED; }
+    const int per_w = (c.dc_max * c.m + c.n) * 4;
     const int budget = d.max_smem - (int)sizeof(Ctrl) - 64;
     int W = std::min(budget / per_w, (int)MAX_W);
     if (want_slots > 0) W = std::min(W, std::max(1, (want_slots + lanes - 1) / lanes));
@@ -101,7 +101,14 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
         double e = double(items) / (double(passes) * t);
         int vp = (c.n + t - 1) / t;
         e = 0.8 * e + 0.2 * double(c.n) / (double(vp) * t);
-        if (e >= best_e - 1e-9) { best_e = e; best_t = t; }
+        if (e > best_e) best_e = e;
+    }
+    for (int t = 128; t <= k.max_threads; t += 32) {
+        int passes = (items + t - 1) / t;
+        double e = double(items) / (double(passes) * t);
+        int vp = (c.n + t - 1) / t;
+        e = 0.8 * e + 0.2 * double(c.n) / (double(vp) * t);
+        if (e >= best_e - 0.03) best_t = t;  // largest CTA within 3% of the best lane efficiency
     }
     if (want_threads > 0) best_t = std::min(k.max_threads, std::max(32, (want_threads / 32) * 32));
     out.kernel = k; out.W = W; out.threads = best_t;
@@ -154,7 +161,7 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     const ldpc_code &c = d.code;
     KParams p;
     p.cdeg = d.d_cdeg; p.vdeg = d.d_vdeg; p.vedge = d.d_vedge;
-    p.n = c.n; p.m = c.m; p.E = c.edges; p.dc_max = c.dc_max; p.dv_max = c.dv_max;
+    p.n = c.n; p.m = c.m; p.E = c.dc_max * c.m; p.dc_max = c.dc_max; p.dv_max = c.dv_max;
     p.W = pl.W; p.max_iter = d.cfg.max_iter; p.precheck = d.cfg.precheck;
     p.llr = llr; p.llr_bits = llr_bits; p.frames = frames;
     p.iters = iters; p.bits = bits; p.nw32 = (c.n + 31) / 32; p.post = post; p.v2c = v2c;

@@ -36,7 +36,7 @@ struct KParams {
     const uint8_t *cdeg;    // [m]
     const uint8_t *vdeg;    // [n]
     const uint16_t *vedge;  // [dv_max][n]  word index (slot*m + check) of edge j of variable v
-    int n, m, E, dc_max, dv_max;
+    int n, m, E, dc_max, dv_max;  // E = dc_max*m words per word set (slot-major, holes for short rows)
     // schedule
     int W;         // word sets per CTA
     int max_iter;  // MAX_ITER
@@ -56,6 +56,15 @@ struct KParams {
     const int *index;
     const int *count;
 };
+
+// prmt with sign-replicating selectors (0xbb99): 0xffff in every 16-bit lane whose sign bit is
+// set.  __byte_perm() masks the replicate bit off the selector, so this has to be PTX.
+__device__ __forceinline__ uint32_t lane_sign_mask(uint32_t x)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xbb99;" : "=r"(r) : "r"(x));
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------
 // lane traits
@@ -142,7 +151,7 @@ struct Packed16 {
     }
     __device__ static __forceinline__ uint32_t neg_c2v(uint32_t o, uint32_t nsign)
     {
-        uint32_t mneg = __byte_perm(~nsign, 0, 0xbb99);  // 0xffff in lanes where c2v > 0
+        uint32_t mneg = lane_sign_mask(~nsign);  // 0xffff in lanes where c2v > 0
         return __vadd2(o, mneg) ^ mneg;                  // ~(o-1) == -o in those lanes
     }
     __device__ static __forceinline__ uint32_t fail_bits(uint32_t acc)
@@ -171,7 +180,7 @@ struct Packed16 {
     __device__ static __forceinline__ uint32_t v2c_word(uint32_t post, uint32_t nc, uint32_t hd, uint32_t &guard)
     {
         uint32_t v = __vadd2(post, nc);
-        uint32_t m = __byte_perm(v, 0, 0xbb99);          // 0xffff in negative lanes
+        uint32_t m = lane_sign_mask(v);                  // 0xffff in negative lanes
         uint32_t t = __vadd2(v, m);                      // v-1 there
         uint32_t ms = t ^ (m & 0x7fff7fffu);             // sign | |v|
         guard |= ms;
