@@ -88,7 +88,7 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
     const ldpc_code &c = d.code;
     if (!k.fn) { set_error("check degree > 64 or variable degree > 32: no kernel instantiation"); return LDPC_ERR_UNSUPPORTED; }
     if ((long long)c.dc_max * c.m > 65535) { set_error("dc_max*m exceeds the 16-bit edge address space"); return LDPC_ERR_UNSUPPORTED; }
-    const int per_w = (c.dc_max * c.m + c.n) * 4;
+    const int per_w = (c.dc_max * c.m + c.n + c.m) * 4;  // messages + channel values + per-check XOR
     const int budget = d.max_smem - (int)sizeof(Ctrl) - 64;
     int W = std::min(budget / per_w, (int)MAX_W);
     if (want_slots > 0) W = std::min(W, std::max(1, (want_slots + lanes - 1) / lanes));

@@ -90,10 +90,11 @@ struct Scalar32 {
         uint32_t u = __vminu2(q, 0x000a000au);
         return (uint32_t)__dp2a_lo((int)u, 0x000001ff, (int)mn);  // mn - u(sum) + u(diff)
     }
-    // word written by the check phase: -c2v where c2v = (sign bit of nsign set) ? -o : +o
-    __device__ static __forceinline__ uint32_t neg_c2v(uint32_t o, uint32_t nsign)
+    // word written by the check phase: -c2v, where c2v = +o if the sign bit of `inv` is set
+    // (inv = ~(XOR of the other incoming words)) and -o otherwise
+    __device__ static __forceinline__ uint32_t neg_c2v(uint32_t o, uint32_t inv)
     {
-        uint32_t mneg = ~(uint32_t)((int)nsign >> 31);  // all ones where c2v > 0 -> store -o
+        uint32_t mneg = (uint32_t)((int)inv >> 31);  // all ones where c2v > 0 -> store -o
         return (o ^ mneg) - mneg;
     }
     __device__ static __forceinline__ uint32_t fail_bits(uint32_t acc) { return (acc >> 30) & 1u; }
@@ -101,10 +102,10 @@ struct Scalar32 {
     struct Acc { int v; };
     __device__ static __forceinline__ Acc acc_init(uint32_t llr) { return Acc{(int)llr}; }
     __device__ static __forceinline__ void acc_sub(Acc &a, uint32_t nc) { a.v -= (int)nc; }
-    // posterior word + hard-decision bits in message position; no guard needed
-    __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd, uint32_t &)
+    // posterior word + its hard decision in message position (bit = post <= 0, quirk Q3)
+    __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd)
     {
-        hd = a.v <= 0 ? HD : 0u;
+        hd = ((uint32_t)(a.v - 1) >> 1) & HD;  // sign of post-1, moved to bit 30
         return (uint32_t)a.v;
     }
     __device__ static __forceinline__ uint32_t v2c_word(uint32_t post, uint32_t nc, uint32_t hd, uint32_t &)
@@ -112,6 +113,7 @@ struct Scalar32 {
         int v = (int)post + (int)nc;
         return (uint32_t)abs(v) | ((uint32_t)v & SIGN) | hd;
     }
+    __device__ static __forceinline__ bool guard_hit(uint32_t) { return false; }
     __device__ static __forceinline__ uint32_t guard_lanes(uint32_t) { return 0u; }
     __device__ static __forceinline__ int lane_value(uint32_t w, int) { return (int)w; }
     __device__ static __forceinline__ int v2c_value(uint32_t w, int)
@@ -143,16 +145,19 @@ struct Packed16 {
     {
         uint32_t mn = __vminu2(a, b);
         uint32_t s = a + b;                      // lanes < 2^15: no carry across
-        uint32_t d = s - 2u * mn;                // |a-b| per lane, no borrow
+        uint32_t d;                              // |a-b| = s - 2*mn per lane, no borrow; on the FMA pipe
+        asm("mad.lo.u32 %0, %1, 0xfffffffe, %2;" : "=r"(d) : "r"(mn), "r"(s));
         uint32_t us = __vminu2(s & 0x00fc00fcu, 0x00280028u);  // 4*min(10,(s&255)>>2)
         uint32_t ud = __vminu2(d & 0x00fc00fcu, 0x00280028u);
-        uint32_t x = 4u * mn + ud - us;          // 4*(mn + u(diff) - u(sum)), lanes < 2^16
+        uint32_t x = 4u * mn + ud;               // 4*(mn + u(diff)), lanes < 2^16
+        // x - us on the FMA pipe (the ALU pipe is the bound resource); every lane stays >= 0
+        asm("mad.lo.u32 %0, %1, 0xffffffff, %0;" : "+r"(x) : "r"(us));
         return x >> 2;                           // low two bits of every lane are zero
     }
-    __device__ static __forceinline__ uint32_t neg_c2v(uint32_t o, uint32_t nsign)
+    __device__ static __forceinline__ uint32_t neg_c2v(uint32_t o, uint32_t inv)
     {
-        uint32_t mneg = lane_sign_mask(~nsign);  // 0xffff in lanes where c2v > 0
-        return __vadd2(o, mneg) ^ mneg;                  // ~(o-1) == -o in those lanes
+        uint32_t mneg = lane_sign_mask(inv);     // 0xffff in lanes where c2v > 0
+        return __vadd2(o, mneg) ^ mneg;          // ~(o-1) == -o in those lanes
     }
     __device__ static __forceinline__ uint32_t fail_bits(uint32_t acc)
     {
@@ -169,13 +174,16 @@ struct Packed16 {
         a.lo = __dp2a_lo((int)nc, 0x000000ff, a.lo);  // -= (int16) low lane
         a.hi = __dp2a_lo((int)nc, 0x0000ff00, a.hi);  // -= (int16) high lane
     }
-    __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd, uint32_t &guard)
+    // Posteriors are summed in 32 bits and clamped to +-CLAMP before packing: a clamped lane still
+    // yields |post + (-c2v)| >= CLAMP - (2^13+9) > 2^13, so the message guard below catches it,
+    // and CLAMP + 2^13 + 9 < 2^15 keeps the packed add from wrapping.
+    static constexpr int CLAMP = 24000;
+    __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd)
     {
-        hd = (a.lo <= 0 ? 0x00004000u : 0u) | (a.hi <= 0 ? 0x40000000u : 0u);
-        // posterior must fit the lane with headroom for post + (-c2v)
-        guard |= ((uint32_t)(a.lo + LIMIT) >= 2u * LIMIT ? 0x00002000u : 0u) |
-                 ((uint32_t)(a.hi + LIMIT) >= 2u * LIMIT ? 0x20000000u : 0u);
-        return __byte_perm((uint32_t)a.lo, (uint32_t)a.hi, 0x5410);
+        const int lo = max(min(a.lo, CLAMP), -CLAMP), hi = max(min(a.hi, CLAMP), -CLAMP);
+        const uint32_t pw = __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
+        hd = (__vadd2(pw, 0xffffffffu) >> 1) & HD;  // sign of post-1 per lane, moved to bit 14
+        return pw;
     }
     __device__ static __forceinline__ uint32_t v2c_word(uint32_t post, uint32_t nc, uint32_t hd, uint32_t &guard)
     {
@@ -186,6 +194,7 @@ struct Packed16 {
         guard |= ms;
         return ms | hd;
     }
+    __device__ static __forceinline__ bool guard_hit(uint32_t guard) { return (guard & GUARD) != 0u; }
     __device__ static __forceinline__ uint32_t guard_lanes(uint32_t guard)
     {
         return ((guard & 0x00006000u) ? 1u : 0u) | ((guard & 0x60000000u) ? 2u : 0u);
@@ -231,25 +240,21 @@ template <int DC> struct LaunchShape {
 // check phase for one check node, messages e[k*m], k < d
 // ------------------------------------------------------------------------------------------
 template <class T, int DC, bool REG>
-__device__ __forceinline__ void check_node(uint32_t *e, int m, int d)
+__device__ __forceinline__ void check_node(uint32_t *e, int m, int d, const uint32_t nacc)
 {
     uint32_t fwd[DC - 1];
     const uint32_t w0 = e[0];
-    uint32_t acc = w0;
     fwd[0] = w0 & T::MAG;
     uint32_t last = fwd[0];  // ends as Forward[d-2] without a runtime-indexed read of fwd[]
 #pragma unroll
-    for (int k = 1; k < DC; ++k) {
-        if (REG || k < d) {
-            uint32_t w = e[k * m];
-            acc ^= w;
-            if (k < DC - 1 && (REG || k < d - 1)) {
-                fwd[k] = T::g(fwd[k - 1], w & T::MAG);
-                last = fwd[k];
-            }
+    for (int k = 1; k < DC - 1; ++k) {
+        if (REG || k < d - 1) {
+            fwd[k] = T::g(fwd[k - 1], e[k * m] & T::MAG);
+            last = fwd[k];
         }
     }
-    // bit 31/15 of acc: parity of the incoming signs.  Outgoing sign of slot k = acc ^ sign_k.
+    // nacc = ~XOR of all incoming words (from the syndrome pass); bit 31/15 of (nacc ^ word_k) is
+    // the inverted sign of the outgoing message of slot k.
     uint32_t bwd = 0;
 #pragma unroll
     for (int k = DC - 1; k >= 1; --k) {
@@ -264,10 +269,73 @@ __device__ __forceinline__ void check_node(uint32_t *e, int m, int d)
                 o = T::g(fwd[k - 1], bwd);  // c2v[k] = sxor(Forward[k-1], Backward[k+1])
                 bwd = T::g(bwd, mag);       // Backward[k]
             }
-            e[k * m] = T::neg_c2v(o, acc ^ w);
+            e[k * m] = T::neg_c2v(o, nacc ^ w);
         }
     }
-    e[0] = T::neg_c2v(bwd, acc ^ w0);  // c2v[0] = Backward[1]
+    e[0] = T::neg_c2v(bwd, nacc ^ w0);  // c2v[0] = Backward[1]
+}
+
+// ------------------------------------------------------------------------------------------
+// variable phase for one variable node of exact degree D, all W word sets
+// (ArrayLDPC_Decoder.cpp:121-156: post = LLR + sum c2v, v2c_j = post - c2v_j)
+// ------------------------------------------------------------------------------------------
+template <class T, int D>
+__device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr,
+                                              int v, int W)
+{
+    uint32_t off[D];  // byte offsets of the D edge words inside a word set
+#pragma unroll
+    for (int j = 0; j < D; ++j) off[j] = (uint32_t)p.vedge[(size_t)j * p.n + v] * 4u;
+    char *base = reinterpret_cast<char *>(edge);
+    const uint32_t stride = (uint32_t)p.E * 4u;
+    for (int w = 0; w < W; ++w, base += stride) {
+        const uint32_t keep = ctrl->keep[w];
+        typename T::Acc acc = T::acc_init(llr[(size_t)w * p.n + v]);
+        uint32_t x[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            x[j] = *reinterpret_cast<uint32_t *>(base + off[j]) & keep;
+            T::acc_sub(acc, x[j]);
+        }
+        uint32_t hd, guard = 0;
+        const uint32_t pw = T::post_word(acc, hd);
+#pragma unroll
+        for (int j = 0; j < D; ++j) *reinterpret_cast<uint32_t *>(base + off[j]) = T::v2c_word(pw, x[j], hd, guard);
+        if (T::guard_hit(guard)) atomicOr(&ctrl->gflag[w], T::guard_lanes(guard));
+        if (p.post) {
+#pragma unroll
+            for (int lane = 0; lane < T::LANES; ++lane) {
+                const int f = ctrl->fid[w * T::LANES + lane];
+                if (f >= 0) p.post[(size_t)f * p.n + v] = T::lane_value(pw, lane);
+            }
+        }
+    }
+}
+
+// any degree (slow path for degrees without an exact instantiation): two passes over the words
+template <class T>
+__device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr,
+                                               int v, int W, int dv)
+{
+    for (int w = 0; w < W; ++w) {
+        uint32_t *ew = edge + (size_t)w * p.E;
+        const uint32_t keep = ctrl->keep[w];
+        typename T::Acc acc = T::acc_init(llr[(size_t)w * p.n + v]);
+        for (int j = 0; j < dv; ++j) T::acc_sub(acc, ew[p.vedge[(size_t)j * p.n + v]] & keep);
+        uint32_t hd, guard = 0;
+        const uint32_t pw = T::post_word(acc, hd);
+        for (int j = 0; j < dv; ++j) {
+            uint32_t *q = &ew[p.vedge[(size_t)j * p.n + v]];
+            *q = T::v2c_word(pw, *q & keep, hd, guard);
+        }
+        if (T::guard_hit(guard)) atomicOr(&ctrl->gflag[w], T::guard_lanes(guard));
+        if (p.post) {
+            for (int lane = 0; lane < T::LANES; ++lane) {
+                const int f = ctrl->fid[w * T::LANES + lane];
+                if (f >= 0) p.post[(size_t)f * p.n + v] = T::lane_value(pw, lane);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -281,11 +349,12 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
     const int n = p.n, m = p.m, E = p.E, W = p.W;
     uint32_t *edge = smem;                // [W][E]
     uint32_t *llr = edge + (size_t)W * E;  // [W][n]
-    Ctrl *ctrl = reinterpret_cast<Ctrl *>(llr + (size_t)W * n);
+    uint32_t *cxor = llr + (size_t)W * n;  // [W][m] inverted XOR of every check's incoming words
+    Ctrl *ctrl = reinterpret_cast<Ctrl *>(cxor + (size_t)W * m);
     const int nslots = W * T::LANES;
     const long long frames = p.count ? (long long)*p.count : p.frames;
 
-    for (int i = tid; i < W * (E + n); i += nthreads) smem[i] = 0u;
+    for (int i = tid; i < W * (E + n + m); i += nthreads) smem[i] = 0u;
     if (tid < MAX_W) { ctrl->fail[tid] = 0u; ctrl->keep[tid] = 0u; ctrl->gflag[tid] = 0u; }
     if (tid < MAX_SLOTS) { ctrl->fid[tid] = -1; ctrl->it[tid] = 0; }
     __syncthreads();
@@ -368,41 +437,28 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
         // (a freshly refilled lane runs it on stale words; its c2v are masked off below)
         for (int i = tid; i < items; i += nthreads) {
             const int w = i / m, c = i - w * m;
-            check_node<T, DC, REG>(edge + (size_t)w * E + c, m, REG ? DC : (int)p.cdeg[c]);
+            check_node<T, DC, REG>(edge + (size_t)w * E + c, m, REG ? DC : (int)p.cdeg[c], cxor[i]);
         }
         __syncthreads();
 
         // ---------------------------------------------------------------- variable phase
         for (int v = tid; v < n; v += nthreads) {
             const int dv = p.vdeg[v];
-            int addr[DV];
-#pragma unroll
-            for (int j = 0; j < DV; ++j) addr[j] = j < dv ? (int)p.vedge[(size_t)j * n + v] : 0;
-            for (int w = 0; w < W; ++w) {
-                uint32_t *ew = edge + (size_t)w * E;
-                const uint32_t keep = ctrl->keep[w];
-                typename T::Acc acc = T::acc_init(llr[(size_t)w * n + v]);
-                uint32_t x[DV];
-#pragma unroll
-                for (int j = 0; j < DV; ++j)
-                    if (j < dv) { x[j] = ew[addr[j]] & keep; T::acc_sub(acc, x[j]); }
-                uint32_t hd, guard = 0;
-                const uint32_t pw = T::post_word(acc, hd, guard);
-#pragma unroll
-                for (int j = 0; j < DV; ++j)
-                    if (j < dv) ew[addr[j]] = T::v2c_word(pw, x[j], hd, guard);
-                if (T::LANES > 1) {
-                    const uint32_t g = T::guard_lanes(guard);
-                    if (g) atomicOr(&ctrl->gflag[w], g);
+            bool done = false;
+            if (DV <= 12) {
+                // exact-degree bodies: no per-edge predicates or branches inside
+                switch (dv) {
+#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1)>(p, ctrl, edge, llr, v, W); done = true; } break;
+                    LDPC_VCASE(1) LDPC_VCASE(2) LDPC_VCASE(3) LDPC_VCASE(4) LDPC_VCASE(5) LDPC_VCASE(6)
+                    LDPC_VCASE(7) LDPC_VCASE(8) LDPC_VCASE(9) LDPC_VCASE(10) LDPC_VCASE(11) LDPC_VCASE(12)
+#undef LDPC_VCASE
+                default: break;
                 }
-                if (p.post) {
-#pragma unroll
-                    for (int lane = 0; lane < T::LANES; ++lane) {
-                        const int f = ctrl->fid[w * T::LANES + lane];
-                        if (f >= 0) p.post[(size_t)f * n + v] = T::lane_value(pw, lane);
-                    }
-                }
+            } else if (dv == DV) {
+                variable_node<T, DV>(p, ctrl, edge, llr, v, W);
+                done = true;
             }
+            if (!done) variable_node_any<T>(p, ctrl, edge, llr, v, W, dv);
         }
         __syncthreads();
 
@@ -421,6 +477,7 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
 #pragma unroll
                 for (int k = 0; k < DC; ++k)
                     if (REG || k < d) acc ^= e[k * m];
+                cxor[i] = ~acc;
                 fb = T::fail_bits(acc);
             }
             const int w0 = __shfl_sync(0xffffffffu, w, 0);
