@@ -1,0 +1,218 @@
+"""Parity tests proper: the CUDA engine through the C ABI vs the C oracle and the golden vectors.
+
+Bit-exact bar (integer path): iteration counts, decoded bits, posteriors and the final
+variable-to-check messages in the reference's EdgeRAM [slot][check] order."""
+import numpy as np
+import pytest
+
+from conftest import channel_frames, tables_of, valid_mask
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # code, Eb/N0 points, frames
+    ("wifi", (2.0, 0.5), 96),
+    ("a5", (4.5, 2.0), 64),
+    ("c79", (4.5, 2.0), 64),
+    ("a24", (6.0, 3.0), 10),
+]
+
+
+def _expect(orc, llr, precheck):
+    return [orc.decode(x, precheck=precheck) for x in llr]
+
+
+def _compare(fp, code, t, out, want, check_state=True):
+    bits = fp.unpack_bits(out["bits"], code.n)
+    mask = valid_mask(t)
+    for f, (it, b, post, edge) in enumerate(want):
+        assert out["iters"][f] == it, ("iters", f, out["iters"][f], it)
+        assert (bits[f] == b).all(), ("bits", f)
+        if check_state and it > 0:  # iters == 0: the reference leaves post / EdgeRAM stale (quirk Q6)
+            assert (out["post"][f] == post).all(), ("post", f)
+            assert (out["v2c"][f][mask] == edge[mask]).all(), ("v2c", f)
+            assert (out["v2c"][f][~mask] == 0).all()
+
+
+@pytest.mark.parametrize("name,snrs,frames", CASES)
+@pytest.mark.parametrize("precision", [32, 16, 0])
+@pytest.mark.parametrize("precheck", [False, True])
+def test_decode_matches_oracle(fp, po, name, snrs, frames, precision, precheck):
+    code = fp.codes.NAMED[name]()
+    t = tables_of(code)
+    orc = po.Oracle(t)
+    rate = fp.codes.INFO_BITS[name] / code.n
+    dec = fp.Decoder(code, precheck=precheck, precision=precision)
+    for snr in snrs:
+        llr = channel_frames(code.n, rate, snr, frames, seed=int(snr * 100) + frames)
+        out = dec.decode(llr, want_post=True, want_v2c=True)
+        _compare(fp, code, t, out, _expect(orc, llr, precheck))
+    assert dec.stats()["kernel_launches"] > 0
+    dec.close()
+
+
+@pytest.mark.parametrize("name,tag,precheck", [("wifi", "wifi_2dB", False), ("wifi", "wifi_0p5dB", False),
+                                               ("a5", "a5_4p5dB", True), ("a5", "a5_2dB", True), ("a24", "a24_3dB", True),
+                                               ("a24", "a24_6dB", True), ("c79", "c79_2dB", False), ("c79", "c79_4p5dB", False)])
+@pytest.mark.parametrize("precision", [32, 0])
+def test_decode_matches_reference_golden(fp, golden, name, tag, precheck, precision):
+    """Vectors dumped from the reference's own FP_Decoder (tests/golden/make_golden.py)."""
+    code = fp.codes.NAMED[name]()
+    t = tables_of(code)
+    mask = valid_mask(t)
+    llr = golden[tag + "_llr"].astype(np.int32)
+    dec = fp.Decoder(code, precheck=precheck, precision=precision)
+    out = dec.decode(llr, want_post=True, want_v2c=True)
+    bits = fp.unpack_bits(out["bits"], code.n)
+    want_bits = np.unpackbits(golden[tag + "_bits"], axis=1)[:, :code.n]
+    assert (out["iters"] == golden[tag + "_iters"]).all()
+    assert (bits == want_bits).all()
+    for f in range(len(llr)):
+        if out["iters"][f] > 0:
+            assert (out["post"][f] == golden[tag + "_post"][f]).all()
+            assert (out["v2c"][f][mask] == golden[tag + "_edge"][f].astype(np.int32)[mask]).all()
+    dec.close()
+
+
+def test_precheck_hits_golden(fp, golden):
+    code = fp.codes.array_p47_r5()
+    llr = golden["a5_9dB_llr"].astype(np.int32)
+    for precision in (32, 16):
+        dec = fp.Decoder(code, precheck=True, precision=precision)
+        out = dec.decode(llr)
+        assert (out["iters"] == golden["a5_9dB_iters"]).all() and (golden["a5_9dB_iters"] == 0).any()
+        assert (fp.unpack_bits(out["bits"], code.n) == np.unpackbits(golden["a5_9dB_bits"], axis=1)[:, :code.n]).all()
+        # without the pre-check the same frames take one iteration (decode_general_fp, quirk Q6)
+        dec2 = fp.Decoder(code, precheck=False, precision=precision)
+        out2 = dec2.decode(llr)
+        assert (out2["iters"][golden["a5_9dB_iters"] == 0] == 1).all()
+        dec.close(); dec2.close()
+
+
+def test_edge_cases(fp, po):
+    code = fp.codes.cut79()
+    t = tables_of(code)
+    orc = po.Oracle(t)
+    dec = fp.Decoder(code)
+    # empty batch
+    out = dec.decode(np.zeros((0, code.n), np.int32))
+    assert out["iters"].shape == (0,)
+    # one frame, odd frame counts (ragged against the two-frames-per-word packing and the slot count)
+    for frames in (1, 3, 11, 257):
+        llr = channel_frames(code.n, 0.86, 3.0, frames, seed=frames)
+        out = dec.decode(llr, want_post=True, want_v2c=True)
+        _compare(fp, code, t, out, _expect(orc, llr, False))
+    # all-zero LLRs: sgn(0) = -1, bit(0) = 1 (quirk Q3); ties everywhere
+    llr = np.zeros((4, code.n), np.int32)
+    out = dec.decode(llr, want_post=True, want_v2c=True)
+    _compare(fp, code, t, out, _expect(orc, llr, False))
+    # +-1 only, and a constant frame
+    rng = np.random.default_rng(0)
+    llr = rng.choice(np.array([-1, 1], np.int32), size=(6, code.n))
+    llr[5] = 7
+    out = dec.decode(llr, want_post=True, want_v2c=True)
+    _compare(fp, code, t, out, _expect(orc, llr, False))
+    dec.close()
+
+
+@pytest.mark.parametrize("name", ["wifi", "a5"])
+def test_guard_fallback_is_exact(fp, po, name):
+    """Values outside the packed kernel's 13-bit range: auto precision must re-decode them exactly in int32,
+    packed-only precision must flag them (iters == -1) instead of returning a wrong answer."""
+    code = fp.codes.NAMED[name]()
+    t = tables_of(code)
+    orc = po.Oracle(t)
+    rate = fp.codes.INFO_BITS[name] / code.n
+    llr = channel_frames(code.n, rate, 2.5, 24, seed=5)
+    llr[::3] *= 40          # |LLR| up to ~2e4: beyond int16 guard, far below the int32 domain limit
+    llr[1::3] *= 9          # borderline: grows past 2^13 during decoding
+    want = _expect(orc, llr, False)
+    dec = fp.Decoder(code, precision=0)
+    out = dec.decode(llr, want_post=True, want_v2c=True)
+    _compare(fp, code, t, out, want)
+    assert dec.stats()["fallback_frames"] >= 8
+    dec16 = fp.Decoder(code, precision=16)
+    out16 = dec16.decode(llr)
+    flagged = out16["iters"] < 0
+    assert flagged[::3].all()
+    ok = ~flagged
+    assert (out16["iters"][ok] == np.array([w[0] for w in want])[ok]).all()
+    dec.close(); dec16.close()
+
+
+def test_max_iter_and_small_configs(fp, po):
+    code = fp.codes.wifi_1944_r12()
+    t = tables_of(code)
+    llr = channel_frames(code.n, 0.5, 1.0, 40, seed=3)
+    for max_iter in (1, 2, 7):
+        orc = po.Oracle(t, max_iter=max_iter)
+        dec = fp.Decoder(code, max_iter=max_iter)
+        out = dec.decode(llr, want_post=True, want_v2c=True)
+        _compare(fp, code, t, out, _expect(orc, llr, False))
+        dec.close()
+    # launch-shape overrides must not change results
+    orc = po.Oracle(t)
+    want = _expect(orc, llr, False)
+    for threads, slots in ((128, 2), (512, 3), (1024, 0)):
+        dec = fp.Decoder(code, threads=threads, frames_per_cta=slots)
+        _compare(fp, code, t, dec.decode(llr, want_post=True, want_v2c=True), want)
+        dec.close()
+
+
+def test_generic_kernel_on_irregular_random_code(fp, po):
+    """A code that matches none of the exact instantiations (falls to the DC<=64 / DV<=32 bucket)."""
+    rng = np.random.default_rng(11)
+    n, m = 600, 200
+    rows = []
+    for c in range(m):
+        d = int(rng.integers(3, 20))
+        rows.append(np.sort(rng.choice(n, d, replace=False)))
+    dc = max(len(r) for r in rows)
+    clist = np.full((m, dc), -1, np.int32)
+    for c, r in enumerate(rows):
+        clist[c, :len(r)] = r
+    code = fp.Code.from_checks(n, [len(r) for r in rows], clist)
+    t = tables_of(code)
+    orc = po.Oracle(t)
+    llr = channel_frames(n, 0.6, 3.0, 40, seed=9)
+    for precision in (32, 0):
+        dec = fp.Decoder(code, precision=precision)
+        _compare(fp, code, t, dec.decode(llr, want_post=True, want_v2c=True), _expect(orc, llr, False))
+        dec.close()
+
+
+def test_full_size_properties(fp, po):
+    """BASELINE-size batch (2^17 frames of the 802.11 code): size-independent properties.
+    (1) the result does not depend on batch composition / slot scheduling: a shuffled batch gives the
+        shuffled result; (2) every frame with iters < 30 satisfies H; (3) a sample equals the oracle;
+    (4) int16 device input == int32 host input."""
+    import torch
+    code = fp.codes.wifi_1944_r12()
+    t = tables_of(code)
+    frames = 1 << 17
+    llr = channel_frames(code.n, 0.5, 1.6, frames, seed=2026)
+    dec = fp.Decoder(code)
+    out = dec.decode(llr)
+    perm = np.random.default_rng(1).permutation(frames)
+    out_p = dec.decode(llr[perm])
+    assert (out_p["iters"] == out["iters"][perm]).all() and (out_p["bits"] == out["bits"][perm]).all()
+    bits = fp.unpack_bits(out["bits"][:4096], code.n)
+    conv = out["iters"][:4096] < 30
+    syn = np.zeros((4096, t.m), np.int32)
+    for k in range(t.dc_max):
+        col = t.clist[:, k]
+        ok = col >= 0
+        syn[:, ok] ^= bits[:, col[ok]]
+    assert (syn[conv] == 0).all() and conv.sum() > 1000
+    orc = po.Oracle(t)
+    sample = np.random.default_rng(2).choice(frames, 64, replace=False)
+    for f in sample:
+        it, b, _, _ = orc.decode(llr[f])
+        assert out["iters"][f] == it and (fp.unpack_bits(out["bits"][f:f + 1], code.n)[0] == b).all()
+    d_llr = torch.from_numpy(llr.astype(np.int16)).cuda()
+    d_iters = torch.zeros(frames, dtype=torch.int32, device="cuda")
+    d_bits = torch.zeros((frames, code.nw32), dtype=torch.int32, device="cuda")
+    dec.decode_device(d_llr.data_ptr(), 16, frames, d_iters.data_ptr(), d_bits.data_ptr())
+    dec.sync()
+    assert (d_iters.cpu().numpy() == out["iters"]).all()
+    assert (d_bits.cpu().numpy().view(np.uint32) == out["bits"]).all()
+    dec.close()
