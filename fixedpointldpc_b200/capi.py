@@ -21,7 +21,9 @@ EXPORTS = (
     "ldpc_code_free", "ldpc_code_dims", "ldpc_code_tables", "ldpc_code_rate", "ldpc_code_save",
     "ldpc_decoder_cfg_default", "ldpc_decoder_create", "ldpc_decoder_destroy", "ldpc_decode_batch",
     "ldpc_decode_batch_device", "ldpc_decoder_sync", "ldpc_decoder_get_stats", "ldpc_device_count",
+    "ldpc_mc_run", "ldpc_mc_run_device", "ldpc_mc_channel",
 )
+STREAM_PHILOX, STREAM_REFERENCE = 1, 2
 
 
 class LdpcError(RuntimeError):
@@ -40,6 +42,17 @@ class DecoderStats(C.Structure):
                 ("threads", C.c_int), ("threads32", C.c_int), ("frames_per_cta", C.c_int),
                 ("frames_per_cta32", C.c_int), ("grid", C.c_int), ("smem_bytes", C.c_int),
                 ("smem_bytes32", C.c_int)]
+
+
+class McCfg(C.Structure):
+    _fields_ = [("snr", C.c_double), ("sigma", C.c_double), ("stream", C.c_int), ("seed", C.c_uint64),
+                ("first_frame", C.c_uint64), ("codeword", C.c_void_p), ("info_index", C.c_void_p),
+                ("info_count", C.c_int), ("pin_index", C.c_void_p), ("pin_count", C.c_int), ("pin_value", C.c_int)]
+
+
+class McCounters(C.Structure):
+    _fields_ = [("frames", C.c_uint64), ("frame_errors", C.c_uint64), ("bit_errors", C.c_uint64),
+                ("iter_sum", C.c_uint64)]
 
 
 _lib = None
@@ -79,6 +92,9 @@ def load_library():
     L.ldpc_decoder_sync.argtypes = [vp]
     L.ldpc_decoder_get_stats.argtypes = [vp, C.POINTER(DecoderStats)]
     L.ldpc_device_count.restype = C.c_int
+    L.ldpc_mc_run.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp, vp, C.POINTER(McCounters)]
+    L.ldpc_mc_run_device.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp, vp, vp, vp]
+    L.ldpc_mc_channel.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp]
     _lib = L
     return L
 
@@ -205,6 +221,50 @@ class Decoder:
 
     def sync(self):
         _check(load_library().ldpc_decoder_sync(self._h))
+
+    # ---- Monte-Carlo mode -------------------------------------------------------------------
+    def _mc_cfg(self, snr, sigma=None, stream=STREAM_PHILOX, seed=1, first_frame=0, codeword=None, info_index=None,
+                pin_index=None, pin_value=0):
+        keep = []
+        cfg = McCfg()
+        cfg.snr = snr
+        cfg.sigma = float(np.sqrt(1.0 / snr)) if sigma is None else sigma
+        cfg.stream, cfg.seed, cfg.first_frame = stream, seed, first_frame
+        if codeword is not None:
+            cw = np.ascontiguousarray(codeword, np.uint8); keep.append(cw); cfg.codeword = cw.ctypes.data
+        if info_index is not None:
+            ii = np.ascontiguousarray(info_index, np.int32); keep.append(ii)
+            cfg.info_index, cfg.info_count = ii.ctypes.data, len(ii)
+        if pin_index is not None and len(pin_index):
+            pi = np.ascontiguousarray(pin_index, np.int32); keep.append(pi)
+            cfg.pin_index, cfg.pin_count, cfg.pin_value = pi.ctypes.data, len(pi), pin_value
+        return cfg, keep
+
+    def mc_run(self, frames, snr, want_frame_err=True, want_iters=False, **kw):
+        """One batch of the drivers' loop body (channel -> decode -> calculateBER) on the GPU.
+        Returns dict(frames, frame_errors, bit_errors, iter_sum, frame_err[frames], iters[frames])."""
+        cfg, keep = self._mc_cfg(snr, **kw)
+        ferr = np.zeros(frames, np.uint16) if want_frame_err else None
+        iters = np.zeros(frames, np.int32) if want_iters else None
+        tot = McCounters()
+        _check(load_library().ldpc_mc_run(self._h, C.byref(cfg), frames, _ptr(ferr), _ptr(iters), C.byref(tot)))
+        del keep
+        return {"frames": tot.frames, "frame_errors": tot.frame_errors, "bit_errors": tot.bit_errors,
+                "iter_sum": tot.iter_sum, "frame_err": ferr, "iters": iters}
+
+    def mc_run_device(self, frames, snr, counters_ptr, frame_err_ptr=None, iters_ptr=None, cuda_stream=None, **kw):
+        cfg, keep = self._mc_cfg(snr, **kw)
+        _check(load_library().ldpc_mc_run_device(self._h, C.byref(cfg), frames, frame_err_ptr, iters_ptr, counters_ptr,
+                                                 cuda_stream))
+        del keep
+
+    def mc_channel(self, frames, snr, **kw):
+        """The quantised LLRs [frames][n] mc_run would decode."""
+        cfg, keep = self._mc_cfg(snr, **kw)
+        out = np.zeros((frames, self.code.n), np.int32)
+        _check(load_library().ldpc_mc_channel(self._h, C.byref(cfg), frames, _ptr(out)))
+        del keep
+        return out
 
     def stats(self):
         s = DecoderStats()

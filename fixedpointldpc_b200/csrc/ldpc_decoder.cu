@@ -78,6 +78,14 @@ struct ldpc_decoder {
     int *d_fb_index = nullptr, *d_fb_count = nullptr;
     unsigned long long *d_fb_total = nullptr;
     size_t fb_cap = 0;
+    // Monte-Carlo mode resources
+    uint32_t *d_mc_pow = nullptr;      // a^(v+1) mod m
+    uint32_t mc_jump = 0;              // a^n mod m
+    uint32_t *d_mc_cw = nullptr, *d_mc_info = nullptr;  // [nw32] each
+    int *d_mc_pin = nullptr; int mc_pin_cap = 0;
+    int *d_mc_iters = nullptr; unsigned short *d_mc_ferr = nullptr; size_t mc_cap = 0;
+    unsigned long long *d_mc_counters = nullptr;
+    int *d_mc_llr = nullptr; size_t mc_llr_cap = 0;
     ldpc_decoder_stats stats;
 };
 
@@ -155,7 +163,7 @@ __global__ void collect_flagged(const int *iters, long long frames, int *index, 
 
 static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, int llr_bits, long long frames,
                   int *iters, uint32_t *bits, int *post, int *v2c, const int *index, const int *count,
-                  cudaStream_t st)
+                  cudaStream_t st, const KParams *mc = nullptr)
 {
     if (frames <= 0) return LDPC_OK;
     const ldpc_code &c = d.code;
@@ -167,6 +175,13 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     p.iters = iters; p.bits = bits; p.nw32 = (c.n + 31) / 32; p.post = post; p.v2c = v2c;
     p.queue = d.d_queue + which;
     p.index = index; p.count = count;
+    p.mc_mode = 0;
+    if (mc) {
+        p.mc_mode = mc->mc_mode; p.mc_first = mc->mc_first; p.mc_seed = mc->mc_seed; p.mc_gain = mc->mc_gain;
+        p.mc_sigma = mc->mc_sigma; p.mc_cw = mc->mc_cw; p.mc_info = mc->mc_info; p.mc_pin = mc->mc_pin;
+        p.mc_pin_count = mc->mc_pin_count; p.mc_pin_value = mc->mc_pin_value; p.mc_pow = mc->mc_pow;
+        p.mc_jump = mc->mc_jump; p.mc_frame_err = mc->mc_frame_err; p.mc_counters = mc->mc_counters;
+    }
     const int lanes = which == 0 ? 2 : 1;
     const long long slots = (long long)pl.W * lanes;
     int grid = (int)std::min<long long>(d.sm_count, (frames + slots - 1) / slots);
@@ -179,15 +194,15 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
 }
 
 static int decode_device(ldpc_decoder &d, const void *llr, int llr_bits, long long frames, int *iters,
-                         uint32_t *bits, int *post, int *v2c, cudaStream_t st)
+                         uint32_t *bits, int *post, int *v2c, cudaStream_t st, const KParams *mc = nullptr)
 {
-    if (llr_bits != 16 && llr_bits != 32) { set_error("llr_bits must be 16 or 32"); return LDPC_ERR_ARG; }
+    if (!mc && llr_bits != 16 && llr_bits != 32) { set_error("llr_bits must be 16 or 32"); return LDPC_ERR_ARG; }
     if (frames > 0x7fffffffLL) { set_error("more than 2^31-1 frames in one call"); return LDPC_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(d.device));
     d.stats.frames += (uint64_t)frames;
     if (d.cfg.precision == 32)
-        return launch(d, d.plan32, 1, llr, llr_bits, frames, iters, bits, post, v2c, nullptr, nullptr, st);
-    int rc = launch(d, d.plan16, 0, llr, llr_bits, frames, iters, bits, post, v2c, nullptr, nullptr, st);
+        return launch(d, d.plan32, 1, llr, llr_bits, frames, iters, bits, post, v2c, nullptr, nullptr, st, mc);
+    int rc = launch(d, d.plan16, 0, llr, llr_bits, frames, iters, bits, post, v2c, nullptr, nullptr, st, mc);
     if (rc != LDPC_OK || d.cfg.precision == 16) return rc;
     // Exact int32 re-decode of the flagged frames, in place and without a host round trip: the
     // second launch reads the frame list and its length from device memory.
@@ -202,8 +217,99 @@ static int decode_device(ldpc_decoder &d, const void *llr, int llr_bits, long lo
     collect_flagged<<<(unsigned)((frames + 255) / 256), 256, 0, st>>>(iters, frames, d.d_fb_index, d.d_fb_count, d.d_fb_total);
     CUDA_TRY(cudaGetLastError());
     d.stats.kernel_launches++;
-    return launch(d, d.plan32, 1, llr, llr_bits, frames, iters, bits, post, v2c, d.d_fb_index, d.d_fb_count, st);
+    return launch(d, d.plan32, 1, llr, llr_bits, frames, iters, bits, post, v2c, d.d_fb_index, d.d_fb_count, st, mc);
 }
+
+// ---- Monte-Carlo mode ------------------------------------------------------------------------
+__global__ void channel_kernel(const KParams p, int *out)
+{
+    for (long long f = blockIdx.x; f < p.frames; f += gridDim.x) {
+        const unsigned long long g = p.mc_first + (unsigned long long)f;
+        int *row = out + (size_t)f * p.n;
+        if (p.mc_mode == 1) {
+            for (int q = threadIdx.x; 4 * q < p.n; q += blockDim.x) {
+                float z[4];
+                philox_normals(p, g, (uint32_t)q, z);
+                for (int h = 0; h < 4; ++h)
+                    if (4 * q + h < p.n) row[4 * q + h] = quantise_llr(p, (double)z[h], cw_bit(p, 4 * q + h));
+            }
+        } else {
+            const uint32_t state = lehmer_mul((uint32_t)p.mc_seed, lehmer_pow(p.mc_jump, g));
+            for (int v = threadIdx.x; v < p.n; v += blockDim.x)
+                row[v] = quantise_llr(p, lehmer_normal(lehmer_mul(state, p.mc_pow[v])), cw_bit(p, v));
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < p.mc_pin_count; i += blockDim.x) row[p.mc_pin[i]] = p.mc_pin_value;
+    }
+}
+
+static int mc_prepare(ldpc_decoder &d, const ldpc_mc_cfg &cfg, KParams &mc, cudaStream_t st)
+{
+    const ldpc_code &c = d.code;
+    const int nw32 = (c.n + 31) / 32;
+    if (cfg.stream != LDPC_STREAM_PHILOX && cfg.stream != LDPC_STREAM_REFERENCE) { set_error("unknown noise stream"); return LDPC_ERR_ARG; }
+    if (!(cfg.snr > 0.0) || !(cfg.sigma > 0.0)) { set_error("snr and sigma must be positive"); return LDPC_ERR_ARG; }
+    if (cfg.stream == LDPC_STREAM_REFERENCE && (cfg.seed == 0 || cfg.seed >= LEHMER_M)) {
+        set_error("Lehmer seed must be in 1..2^31-2 (rngs.cpp:45)"); return LDPC_ERR_ARG;
+    }
+    if (!d.d_mc_pow) {
+        std::vector<uint32_t> pw(c.n);
+        uint32_t x = 1;
+        for (int v = 0; v < c.n; ++v) { x = lehmer_mul(x, 48271u); pw[v] = x; }  // MULTIPLIER, rngs.cpp:41
+        d.mc_jump = x;
+        CUDA_TRY(cudaMalloc(&d.d_mc_pow, c.n * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpy(d.d_mc_pow, pw.data(), c.n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&d.d_mc_cw, nw32 * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&d.d_mc_info, nw32 * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&d.d_mc_counters, 4 * sizeof(unsigned long long)));
+    }
+    std::vector<uint32_t> cw(nw32, 0u), info(nw32, 0u);
+    if (cfg.codeword)
+        for (int v = 0; v < c.n; ++v) if (cfg.codeword[v] & 1) cw[v >> 5] |= 1u << (v & 31);
+    if (cfg.info_index) {
+        for (int i = 0; i < cfg.info_count; ++i) {
+            const int v = cfg.info_index[i];
+            if (v < 0 || v >= c.n) { set_error("info_index out of range"); return LDPC_ERR_ARG; }
+            info[v >> 5] |= 1u << (v & 31);
+        }
+    } else {
+        for (int v = 0; v < c.n; ++v) info[v >> 5] |= 1u << (v & 31);
+    }
+    CUDA_TRY(cudaMemcpyAsync(d.d_mc_cw, cw.data(), nw32 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d.d_mc_info, info.data(), nw32 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (cfg.pin_count > 0) {
+        if (!cfg.pin_index) { set_error("pin_index is NULL"); return LDPC_ERR_ARG; }
+        for (int i = 0; i < cfg.pin_count; ++i)
+            if (cfg.pin_index[i] < 0 || cfg.pin_index[i] >= c.n) { set_error("pin_index out of range"); return LDPC_ERR_ARG; }
+        if (d.mc_pin_cap < cfg.pin_count) {
+            cudaFree(d.d_mc_pin); d.d_mc_pin = nullptr; d.mc_pin_cap = 0;
+            CUDA_TRY(cudaMalloc(&d.d_mc_pin, cfg.pin_count * sizeof(int)));
+            d.mc_pin_cap = cfg.pin_count;
+        }
+        CUDA_TRY(cudaMemcpyAsync(d.d_mc_pin, cfg.pin_index, cfg.pin_count * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));  // the staging vectors above go out of scope
+    mc.mc_mode = cfg.stream; mc.mc_first = cfg.first_frame; mc.mc_seed = cfg.seed;
+    mc.mc_gain = 2 * cfg.snr; mc.mc_sigma = cfg.sigma;
+    mc.mc_cw = cfg.codeword ? d.d_mc_cw : nullptr; mc.mc_info = d.d_mc_info;
+    mc.mc_pin = d.d_mc_pin; mc.mc_pin_count = cfg.pin_count > 0 ? cfg.pin_count : 0; mc.mc_pin_value = cfg.pin_value;
+    mc.mc_pow = d.d_mc_pow; mc.mc_jump = d.mc_jump;
+    mc.mc_frame_err = nullptr; mc.mc_counters = d.d_mc_counters;
+    mc.n = c.n;
+    return LDPC_OK;
+}
+
+static int mc_scratch(ldpc_decoder &d, size_t frames)
+{
+    if (d.mc_cap >= frames) return LDPC_OK;
+    cudaFree(d.d_mc_iters); cudaFree(d.d_mc_ferr);
+    d.d_mc_iters = nullptr; d.d_mc_ferr = nullptr; d.mc_cap = 0;
+    CUDA_TRY(cudaMalloc(&d.d_mc_iters, frames * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d.d_mc_ferr, frames * sizeof(unsigned short)));
+    d.mc_cap = frames;
+    return LDPC_OK;
+}
+
 
 static void free_staging(ldpc_decoder &d)
 {
@@ -368,6 +474,8 @@ void ldpc_decoder_destroy(ldpc_decoder *d)
     ldpc::free_staging(*d);
     cudaFree(d->d_cdeg); cudaFree(d->d_vdeg); cudaFree(d->d_vedge); cudaFree(d->d_queue);
     cudaFree(d->d_fb_index); cudaFree(d->d_fb_count); cudaFree(d->d_fb_total);
+    cudaFree(d->d_mc_pow); cudaFree(d->d_mc_cw); cudaFree(d->d_mc_info); cudaFree(d->d_mc_pin);
+    cudaFree(d->d_mc_iters); cudaFree(d->d_mc_ferr); cudaFree(d->d_mc_counters); cudaFree(d->d_mc_llr);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
@@ -399,6 +507,70 @@ int ldpc_decode_batch(ldpc_decoder *d, const int32_t *llr, size_t frames, int32_
     if (bits) CUDA_TRY(cudaMemcpyAsync(bits, d->d_bits, frames * nw32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     if (post) CUDA_TRY(cudaMemcpyAsync(post, d->d_post, frames * c.n * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (v2c) CUDA_TRY(cudaMemcpyAsync(v2c, d->d_v2c, frames * vsz * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return LDPC_OK;
+}
+
+int ldpc_mc_run_device(ldpc_decoder *d, const ldpc_mc_cfg *cfg, size_t frames, uint16_t *d_frame_err,
+                       int32_t *d_iters, uint64_t *d_counters, void *stream)
+{
+    if (!d || !cfg) { ldpc::set_error("NULL decoder / cfg"); return LDPC_ERR_ARG; }
+    if (frames == 0) return LDPC_OK;
+    CUDA_TRY(cudaSetDevice(d->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    ldpc::KParams mc;
+    int rc = ldpc::mc_prepare(*d, *cfg, mc, st);
+    if (rc != LDPC_OK) return rc;
+    if (!d_iters) {  // the fallback list is built from the iteration counts, so they always exist
+        if ((rc = ldpc::mc_scratch(*d, frames)) != LDPC_OK) return rc;
+        d_iters = d->d_mc_iters;
+    }
+    mc.mc_frame_err = d_frame_err;
+    if (d_counters) mc.mc_counters = (unsigned long long *)d_counters;
+    else CUDA_TRY(cudaMemsetAsync(d->d_mc_counters, 0, 4 * sizeof(unsigned long long), st));
+    return ldpc::decode_device(*d, nullptr, 32, (long long)frames, d_iters, nullptr, nullptr, nullptr, st, &mc);
+}
+
+int ldpc_mc_run(ldpc_decoder *d, const ldpc_mc_cfg *cfg, size_t frames, uint16_t *frame_err, int32_t *iters,
+                ldpc_mc_counters *totals)
+{
+    if (!d || !cfg) { ldpc::set_error("NULL decoder / cfg"); return LDPC_ERR_ARG; }
+    if (totals) std::memset(totals, 0, sizeof *totals);
+    if (frames == 0) return LDPC_OK;
+    CUDA_TRY(cudaSetDevice(d->device));
+    int rc = ldpc::mc_scratch(*d, frames);
+    if (rc != LDPC_OK) return rc;
+    cudaStream_t st = d->stream;
+    rc = ldpc_mc_run_device(d, cfg, frames, d->d_mc_ferr, d->d_mc_iters, nullptr, st);
+    if (rc != LDPC_OK) return rc;
+    if (frame_err) CUDA_TRY(cudaMemcpyAsync(frame_err, d->d_mc_ferr, frames * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    if (iters) CUDA_TRY(cudaMemcpyAsync(iters, d->d_mc_iters, frames * sizeof(int), cudaMemcpyDeviceToHost, st));
+    unsigned long long c[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(c, d->d_mc_counters, sizeof c, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (totals) { totals->frames = c[0]; totals->frame_errors = c[1]; totals->bit_errors = c[2]; totals->iter_sum = c[3]; }
+    return LDPC_OK;
+}
+
+int ldpc_mc_channel(ldpc_decoder *d, const ldpc_mc_cfg *cfg, size_t frames, int32_t *llr)
+{
+    if (!d || !cfg || !llr) { ldpc::set_error("NULL decoder / cfg / llr"); return LDPC_ERR_ARG; }
+    if (frames == 0) return LDPC_OK;
+    CUDA_TRY(cudaSetDevice(d->device));
+    cudaStream_t st = d->stream;
+    ldpc::KParams mc;
+    int rc = ldpc::mc_prepare(*d, *cfg, mc, st);
+    if (rc != LDPC_OK) return rc;
+    if (d->mc_llr_cap < frames) {
+        cudaFree(d->d_mc_llr); d->d_mc_llr = nullptr; d->mc_llr_cap = 0;
+        CUDA_TRY(cudaMalloc(&d->d_mc_llr, frames * d->code.n * sizeof(int)));
+        d->mc_llr_cap = frames;
+    }
+    mc.frames = (long long)frames;
+    ldpc::channel_kernel<<<(unsigned)std::min<size_t>(frames, 4096), 256, 0, st>>>(mc, d->d_mc_llr);
+    CUDA_TRY(cudaGetLastError());
+    d->stats.kernel_launches++;
+    CUDA_TRY(cudaMemcpyAsync(llr, d->d_mc_llr, frames * d->code.n * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return LDPC_OK;
 }

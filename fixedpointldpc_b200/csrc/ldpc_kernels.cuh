@@ -55,6 +55,21 @@ struct KParams {
     // position q decodes frame index[q], and the number of positions is *count
     const int *index;
     const int *count;
+    // Monte-Carlo mode: the channel values are generated in the refill step instead of read from
+    // memory and the finish step counts errors instead of (or besides) storing bits.
+    int mc_mode;                   // 0 off, 1 Philox4x32-10 counter stream, 2 the reference's Lehmer stream
+    unsigned long long mc_first;   // global index of frame 0 of this launch
+    unsigned long long mc_seed;    // Philox key / Lehmer state before global frame 0
+    double mc_gain;                // 2*snr   (LLR = 2*snr*(1 - 2c + N(0,sigma)), PerfTest.cpp:112)
+    double mc_sigma;
+    const uint32_t *mc_cw;         // [nw32] transmitted codeword bits or NULL (all-zero codeword)
+    const uint32_t *mc_info;       // [nw32] positions calculateBER counts (ArrayLDPC_Decoder.cpp:707-722)
+    const int *mc_pin;             // shortening: LLR_fp[pin[i]] = pin_value (PerfTest.cpp:410-414)
+    int mc_pin_count, mc_pin_value;
+    const uint32_t *mc_pow;        // [n] a^(v+1) mod (2^31-1)  (mode 2)
+    uint32_t mc_jump;              // a^n mod (2^31-1): one frame consumes n uniforms (mode 2)
+    unsigned short *mc_frame_err;  // [frames] info-bit errors per frame (saturating) or NULL
+    unsigned long long *mc_counters;  // frames, frame errors, bit errors, iteration sum
 };
 
 // prmt with sign-replicating selectors (0xbb99): 0xffff in every 16-bit lane whose sign bit is
@@ -219,6 +234,95 @@ struct Packed16 {
 };
 
 // ------------------------------------------------------------------------------------------
+// channel: BPSK + AWGN + the reference's quantiser LLR_fp = int(2*snr*(1 - 2c + N(0,sigma)) * 2^4)
+// (PerfTest.cpp:108-120, 164-170, 287-297, 494-504), truncation toward zero, no clipping (Q11)
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t LEHMER_M = 2147483647u;  // rngs.cpp:40
+
+__host__ __device__ __forceinline__ uint32_t lehmer_mul(uint32_t a, uint32_t b)
+{
+    unsigned long long p = (unsigned long long)a * b;
+    p = (p & LEHMER_M) + (p >> 31);
+    p = (p & LEHMER_M) + (p >> 31);
+    return (uint32_t)(p >= LEHMER_M ? p - LEHMER_M : p);
+}
+
+__host__ __device__ __forceinline__ uint32_t lehmer_pow(uint32_t base, unsigned long long e)
+{
+    uint32_t r = 1u;
+    while (e) {
+        if (e & 1ull) r = lehmer_mul(r, base);
+        base = lehmer_mul(base, base);
+        e >>= 1;
+    }
+    return r;
+}
+
+// rvgs.cpp:152-181 (Odeh-Evans inverse normal) on the uniform rngs.cpp:52-69 returns for `state`.
+// Written with explicit round-to-nearest multiplies/adds so nvcc cannot contract them into FMAs:
+// the reference build evaluates every product and sum separately.
+__device__ __forceinline__ double lehmer_normal(uint32_t state)
+{
+    const double u = (double)state / 2147483647.0;
+    const double t = u < 0.5 ? sqrt(__dmul_rn(-2.0, log(u))) : sqrt(__dmul_rn(-2.0, log(__dsub_rn(1.0, u))));
+    double pn = __dadd_rn(0.204231210245e-1, __dmul_rn(t, 0.453642210148e-4));
+    pn = __dadd_rn(0.342242088547, __dmul_rn(t, pn));
+    pn = __dadd_rn(1.0, __dmul_rn(t, pn));
+    pn = __dadd_rn(0.322232431088, __dmul_rn(t, pn));
+    double qn = __dadd_rn(0.103537752850, __dmul_rn(t, 0.385607006340e-2));
+    qn = __dadd_rn(0.531103462366, __dmul_rn(t, qn));
+    qn = __dadd_rn(0.588581570495, __dmul_rn(t, qn));
+    qn = __dadd_rn(0.099348462606, __dmul_rn(t, qn));
+    const double ratio = __ddiv_rn(pn, qn);
+    return u < 0.5 ? __dsub_rn(ratio, t) : __dsub_rn(t, ratio);
+}
+
+__device__ __forceinline__ int quantise_llr(const KParams &p, double z, uint32_t bit)
+{
+    // 2*snr*(1 - 2*c + (0 + sigma*z)) * 16, in the reference's evaluation order
+    const double noise = __dadd_rn(0.0, __dmul_rn(p.mc_sigma, z));
+    const double x = __dadd_rn(bit ? -1.0 : 1.0, noise);
+    return (int)__dmul_rn(__dmul_rn(p.mc_gain, x), 16.0);
+}
+
+struct Philox4 { uint32_t x[4]; };
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return Philox4{{c0, c1, c2, c3}};
+}
+
+// four standard normals for variables 4*q..4*q+3 of global frame g: two Box-Muller pairs
+__device__ __forceinline__ void philox_normals(const KParams &p, unsigned long long g, uint32_t q, float z[4])
+{
+    const Philox4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), q, 0x4c445043u, (uint32_t)p.mc_seed,
+                                    (uint32_t)(p.mc_seed >> 32));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float u1 = ((float)(r.x[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1), 24 bits
+        const float u2 = ((float)(r.x[2 * h + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float rad = sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        z[2 * h] = rad * cs;
+        z[2 * h + 1] = rad * sn;
+    }
+}
+
+__device__ __forceinline__ uint32_t cw_bit(const KParams &p, int v)
+{
+    return p.mc_cw ? (p.mc_cw[v >> 5] >> (v & 31)) & 1u : 0u;
+}
+
+// ------------------------------------------------------------------------------------------
 // control block in shared memory (after the message and channel words)
 // ------------------------------------------------------------------------------------------
 constexpr int MAX_W = 16;         // word sets per CTA
@@ -230,6 +334,8 @@ struct Ctrl {
     uint32_t gflag[MAX_W];  // per word set: lanes that left the guard range (Packed16)
     int fid[MAX_SLOTS];     // frame index decoded in the slot, -1 = idle
     int it[MAX_SLOTS];      // iterations completed by that frame
+    uint32_t lehmer[MAX_SLOTS];  // Lehmer state before the slot's frame (MC mode 2)
+    unsigned int errs;      // info-bit errors of the frame being finished (MC mode)
 };
 
 template <int DC> struct LaunchShape {
@@ -375,7 +481,9 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
                     const bool overflow = (ctrl->gflag[w] >> lane) & 1u;
                     if (tid == 0) p.iters[f] = overflow ? -1 : ctrl->it[s];
                     const uint32_t *ew = edge + (size_t)w * E;
-                    if (p.bits) {
+                    const bool count_errors = p.mc_mode != 0 && !overflow;
+                    if (p.bits || count_errors) {
+                        unsigned int errs = 0;
                         for (int v0 = 0; v0 < n; v0 += nthreads) {
                             const int v = v0 + tid;
                             uint32_t b = 0;
@@ -384,7 +492,28 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
                                 else b = T::lane_value(llr[(size_t)w * n + v], lane) <= 0;
                             }
                             const uint32_t word = __ballot_sync(0xffffffffu, b);
-                            if (lane_id == 0 && v < n) p.bits[(size_t)f * p.nw32 + (v >> 5)] = word;
+                            if (lane_id == 0 && v < n) {
+                                if (p.bits) p.bits[(size_t)f * p.nw32 + (v >> 5)] = word;
+                                if (count_errors) {
+                                    const uint32_t sent = p.mc_cw ? p.mc_cw[v >> 5] : 0u;
+                                    const uint32_t mask = p.mc_info ? p.mc_info[v >> 5] : 0xffffffffu;
+                                    errs += __popc((word ^ sent) & mask);
+                                }
+                            }
+                        }
+                        if (count_errors) {
+                            if (tid == 0) ctrl->errs = 0u;
+                            __syncthreads();
+                            if (errs) atomicAdd(&ctrl->errs, errs);
+                            __syncthreads();
+                            if (tid == 0) {
+                                const unsigned int e = ctrl->errs;
+                                if (p.mc_frame_err) p.mc_frame_err[f] = (unsigned short)min(e, 65535u);
+                                atomicAdd(&p.mc_counters[0], 1ull);
+                                if (e) atomicAdd(&p.mc_counters[1], 1ull);
+                                if (e) atomicAdd(&p.mc_counters[2], (unsigned long long)e);
+                                atomicAdd(&p.mc_counters[3], (unsigned long long)ctrl->it[s]);
+                            }
                         }
                     }
                     if (p.v2c) {
@@ -403,6 +532,9 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
                     const int w = s / T::LANES, lane = s % T::LANES;
                     const unsigned long long f = atomicAdd(p.queue, 1ull);
                     ctrl->fid[s] = f < (unsigned long long)frames ? (p.index ? p.index[f] : (int)f) : -1;
+                    if (p.mc_mode == 2 && ctrl->fid[s] >= 0)
+                        ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed,
+                                                     lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)ctrl->fid[s]));
                     ctrl->it[s] = 0;
                     ctrl->keep[w] &= ~T::lane_mask(lane);  // fresh: the next variable phase sees c2v == 0
                     ctrl->gflag[w] &= ~(1u << lane);
@@ -414,15 +546,45 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
                 const int w = s / T::LANES, lane = s % T::LANES;
                 const int f = ctrl->fid[s];
                 bool any_bad = false;
-                for (int v = tid; v < n; v += nthreads) {
-                    int val = 0;
-                    if (f >= 0)
-                        val = p.llr_bits == 16 ? (int)reinterpret_cast<const int16_t *>(p.llr)[(size_t)f * n + v]
-                                               : reinterpret_cast<const int *>(p.llr)[(size_t)f * n + v];
-                    bool bad;
-                    uint32_t *dst = &llr[(size_t)w * n + v];
-                    *dst = T::set_lane(*dst, lane, val, bad);
-                    any_bad |= bad;
+                if (p.mc_mode == 1 && f >= 0) {
+                    const unsigned long long g = p.mc_first + (unsigned long long)f;
+                    for (int q = tid; 4 * q < n; q += nthreads) {
+                        float z[4];
+                        philox_normals(p, g, (uint32_t)q, z);
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const int v = 4 * q + h;
+                            if (v < n) {
+                                bool bad;
+                                uint32_t *dst = &llr[(size_t)w * n + v];
+                                *dst = T::set_lane(*dst, lane, quantise_llr(p, (double)z[h], cw_bit(p, v)), bad);
+                                any_bad |= bad;
+                            }
+                        }
+                    }
+                } else {
+                    for (int v = tid; v < n; v += nthreads) {
+                        int val = 0;
+                        if (f >= 0) {
+                            if (p.mc_mode == 2)
+                                val = quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], p.mc_pow[v])), cw_bit(p, v));
+                            else
+                                val = p.llr_bits == 16 ? (int)reinterpret_cast<const int16_t *>(p.llr)[(size_t)f * n + v]
+                                                       : reinterpret_cast<const int *>(p.llr)[(size_t)f * n + v];
+                        }
+                        bool bad;
+                        uint32_t *dst = &llr[(size_t)w * n + v];
+                        *dst = T::set_lane(*dst, lane, val, bad);
+                        any_bad |= bad;
+                    }
+                }
+                if (p.mc_mode != 0 && p.mc_pin_count > 0 && f >= 0) {
+                    __syncthreads();
+                    for (int i = tid; i < p.mc_pin_count; i += nthreads) {
+                        bool bad;
+                        uint32_t *dst = &llr[(size_t)w * n + p.mc_pin[i]];
+                        *dst = T::set_lane(*dst, lane, p.mc_pin_value, bad);
+                    }
                 }
                 if (any_bad) atomicOr(&ctrl->gflag[w], 1u << lane);
             }

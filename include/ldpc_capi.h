@@ -137,6 +137,58 @@ typedef struct {
 
 int ldpc_decoder_get_stats(const ldpc_decoder *dec, ldpc_decoder_stats *out);
 
+/* ------------------------------------------------------------------ Monte-Carlo mode (device) */
+
+/* Noise streams. */
+enum {
+    LDPC_STREAM_PHILOX = 1,   /* counter-based Philox4x32-10, counter = (global frame, variable/4) */
+    LDPC_STREAM_REFERENCE = 2 /* the reference's own stream: Lehmer LCG rngs.cpp:52-69 + Odeh-Evans
+                                 Normal rvgs.cpp:152-181, one uniform per bit, regenerated in parallel by
+                                 O(log) skip-ahead; reproduces the reference's frames bit for bit */
+};
+
+/* One simulation point == the loop body of ArrayLDPC_Debug_Wifi / ArrayLDPC_Debug / ArrayLDPC_PerfTest /
+ * ArrayLDPC_Debug_Shorten (PerfTest.cpp:97-135, 276-311, 385-426, 491-512): BPSK + AWGN + quantiser
+ * (LLR_fp = int(2*snr*(1 - 2c + N(0,sigma)) * 2^4), truncation, no clipping), decode, calculateBER. */
+typedef struct {
+    double snr;                /* the drivers' `snr` / `EbN0` variable: 2*10^(dB/10)*R (PerfTest.cpp:62,159,253,487) */
+    double sigma;              /* sqrt(1/snr) */
+    int stream;                /* LDPC_STREAM_*                                                          */
+    uint64_t seed;             /* Philox key, or the Lehmer state before global frame 0 (rngs.cpp:45: 123456789) */
+    uint64_t first_frame;      /* global index of the first frame of this call (frames are independent)  */
+    const uint8_t *codeword;   /* [n] transmitted bits, NULL = all-zero codeword                         */
+    const int32_t *info_index; /* [info_count] positions calculateBER compares (ArrayLDPC_Decoder.cpp:707-722),
+                                  NULL = all n positions                                                  */
+    int info_count;
+    const int32_t *pin_index;  /* shortening: LLR_fp[pin_index[i]] = pin_value after the channel
+                                  (ArrayLDPC_Debug_Shorten, PerfTest.cpp:410-414)                         */
+    int pin_count;
+    int pin_value;
+} ldpc_mc_cfg;
+
+typedef struct {
+    uint64_t frames;       /* Counter                                                */
+    uint64_t frame_errors; /* pckerror: frames with at least one info-bit error      */
+    uint64_t bit_errors;   /* biterror                                               */
+    uint64_t iter_sum;     /* sum of the decoder's return values                     */
+} ldpc_mc_counters;
+
+/* Simulates `frames` frames starting at cfg->first_frame.  Host outputs (any may be NULL):
+ *   frame_err [frames] info-bit errors of every frame (saturating at 65535), in frame order, so the caller
+ *             can apply the reference's sequential stopping rule `while(pckerror < 100)` exactly;
+ *   iters     [frames] the decoder's return value per frame;
+ *   totals    sums over the call. */
+int ldpc_mc_run(ldpc_decoder *dec, const ldpc_mc_cfg *cfg, size_t frames, uint16_t *frame_err, int32_t *iters,
+                ldpc_mc_counters *totals);
+
+/* Same with DEVICE outputs, asynchronous on `stream`: d_counters is uint64[4] in ldpc_mc_counters order and is
+ * accumulated into (the caller zeroes it). */
+int ldpc_mc_run_device(ldpc_decoder *dec, const ldpc_mc_cfg *cfg, size_t frames, uint16_t *d_frame_err,
+                       int32_t *d_iters, uint64_t *d_counters, void *stream);
+
+/* Channel only: the quantised LLRs [frames][n] the simulation above would decode (host buffer). */
+int ldpc_mc_channel(ldpc_decoder *dec, const ldpc_mc_cfg *cfg, size_t frames, int32_t *llr);
+
 /* Number of CUDA devices visible, or a negative status. */
 int ldpc_device_count(void);
 

@@ -1,0 +1,142 @@
+"""Monte-Carlo mode (fused channel + decode + calculateBER) on the GPU."""
+import numpy as np
+import pytest
+
+from conftest import tables_of
+
+pytestmark = pytest.mark.gpu
+
+WIFI_SNR_2DB = 2 * 10 ** (2.0 / 10) * 0.5
+
+
+def test_reference_stream_channel_is_bit_exact(fp, golden, po):
+    """LDPC_STREAM_REFERENCE regenerates the reference's Lehmer/Odeh-Evans noise in parallel: the first frames
+    of the ArrayLDPC_Debug_Wifi flow (default seed, PerfTest.cpp:108-120) must come out bit for bit."""
+    code = fp.codes.wifi_1944_r12()
+    dec = fp.Decoder(code)
+    cw = golden["wifi_codeword"]
+    llr = dec.mc_channel(24, WIFI_SNR_2DB, stream=fp.STREAM_REFERENCE, seed=123456789, codeword=cw)
+    assert (llr == golden["wifi_2dB_llr"]).all()
+    # skip-ahead: frames 10..23 generated on their own
+    part = dec.mc_channel(14, WIFI_SNR_2DB, stream=fp.STREAM_REFERENCE, seed=123456789, codeword=cw, first_frame=10)
+    assert (part == golden["wifi_2dB_llr"][10:]).all()
+    # a long stretch against the oracle's sequential generator (also pins the FMA-free arithmetic)
+    orc = po.Oracle(None)
+    orc.seed.value = 123456789
+    want = np.array([orc.channel_frame(cw.astype(np.int32), code.n, WIFI_SNR_2DB, np.sqrt(1 / WIFI_SNR_2DB)) for _ in range(400)])
+    assert (dec.mc_channel(400, WIFI_SNR_2DB, stream=fp.STREAM_REFERENCE, seed=123456789, codeword=cw) == want).all()
+    dec.close()
+
+
+def test_reference_stream_simulation_matches_golden_flow(fp, golden):
+    code = fp.codes.wifi_1944_r12()
+    dec = fp.Decoder(code)
+    out = dec.mc_run(24, WIFI_SNR_2DB, stream=fp.STREAM_REFERENCE, seed=123456789, codeword=golden["wifi_codeword"],
+                     info_index=golden["wifi_info_index"], want_iters=True)
+    assert (out["iters"] == golden["wifi_2dB_iters"]).all()
+    assert (out["frame_err"] == golden["wifi_2dB_ber"]).all()
+    assert out["frames"] == 24 and out["iter_sum"] == golden["wifi_2dB_iters"].sum()
+    # array code, decode_fixpoint flow (ArrayLDPC_Debug, PerfTest.cpp:276-311)
+    a5 = fp.codes.array_p47_r5()
+    dec5 = fp.Decoder(a5, precheck=True)
+    snr = 2 * 10 ** (4.5 / 10) * a5.rate
+    out = dec5.mc_run(24, snr, stream=fp.STREAM_REFERENCE, seed=123456789, codeword=golden["a5_codeword"],
+                      info_index=golden["a5_info_index"], want_iters=True)
+    assert (out["iters"] == golden["a5_4p5dB_iters"]).all()
+    llr = dec5.mc_channel(24, snr, stream=fp.STREAM_REFERENCE, seed=123456789, codeword=golden["a5_codeword"])
+    assert (llr == golden["a5_4p5dB_llr"]).all()
+    dec.close(); dec5.close()
+
+
+def test_wifi_results_transcript_reproduced_on_gpu(fp, golden):
+    """wifi_results_4_4_2dB_30iter.txt: `2732 100 393214` (bit errors, frame errors, frames) for
+    ArrayLDPC_Debug_Wifi at 2 dB with the default seed, stopping at the 100th frame error."""
+    code = fp.codes.wifi_1944_r12()
+    dec = fp.Decoder(code)
+    frame_errors = bit_errors = counter = 0
+    batch, first = 1 << 16, 0
+    done = False
+    while not done:
+        out = dec.mc_run(batch, WIFI_SNR_2DB, stream=fp.STREAM_REFERENCE, seed=123456789, first_frame=first,
+                         codeword=golden["wifi_codeword"], info_index=golden["wifi_info_index"])
+        for e in out["frame_err"]:          # the reference's sequential stopping rule (PerfTest.cpp:97,131-134)
+            counter += 1
+            if e:
+                frame_errors += 1
+                bit_errors += int(e)
+                if frame_errors == 100:
+                    done = True
+                    break
+        first += batch
+        assert first < 1 << 20
+    assert (bit_errors, frame_errors, counter) == (2732, 100, 393214)
+    assert "%g %g" % (frame_errors / counter, bit_errors / counter / 1944) == "0.000254314 3.57401e-06"
+    dec.close()
+
+
+def test_philox_stream_statistics_and_determinism(fp):
+    code = fp.codes.cut79()
+    dec = fp.Decoder(code)
+    snr = 2 * 10 ** (3.0 / 10) * 0.8585
+    sigma = np.sqrt(1 / snr)
+    a = dec.mc_channel(512, snr, stream=fp.STREAM_PHILOX, seed=77)
+    b = dec.mc_channel(512, snr, stream=fp.STREAM_PHILOX, seed=77)
+    assert (a == b).all()
+    c = dec.mc_channel(100, snr, stream=fp.STREAM_PHILOX, seed=77, first_frame=200)
+    assert (c == a[200:300]).all()                      # frame g depends on (seed, g) only
+    assert (dec.mc_channel(64, snr, stream=fp.STREAM_PHILOX, seed=78) != a[:64]).mean() > 0.9
+    z = (a.astype(np.float64) + 0.5 * np.sign(a)) / (2 * snr * 16) - 1.0   # undo the quantiser (mid-point)
+    z /= sigma
+    nsamp = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(nsamp) + 2e-3
+    assert abs(z.var() - 1.0) < 0.01
+    assert abs((z ** 4).mean() - 3.0) < 0.05
+    assert abs(np.corrcoef(z[:, :-1].ravel(), z[:, 1:].ravel())[0, 1]) < 5 / np.sqrt(nsamp)
+    assert (np.abs(z) > 4).mean() == pytest.approx(6.33e-5, rel=0.5)
+    dec.close()
+
+
+@pytest.mark.parametrize("name,precheck,snr_db", [("wifi", False, 1.4), ("a5", True, 3.6)])
+def test_simulation_equals_decode_of_its_own_channel(fp, po, name, precheck, snr_db):
+    """mc_run == decode_batch(mc_channel) + host-side calculateBER, with a non-zero codeword and info positions."""
+    code = fp.codes.NAMED[name]()
+    t = tables_of(code)
+    rng = np.random.default_rng(4)
+    # a valid codeword is not needed for the bookkeeping identity; use random bits and random info positions
+    cw = rng.integers(0, 2, code.n).astype(np.uint8)
+    info = np.sort(rng.choice(code.n, fp.codes.INFO_BITS[name], replace=False)).astype(np.int32)
+    snr = 2 * 10 ** (snr_db / 10) * fp.codes.INFO_BITS[name] / code.n
+    dec = fp.Decoder(code, precheck=precheck)
+    frames = 600
+    sim = dec.mc_run(frames, snr, stream=fp.STREAM_PHILOX, seed=5, first_frame=1000, codeword=cw, info_index=info,
+                     want_iters=True)
+    llr = dec.mc_channel(frames, snr, stream=fp.STREAM_PHILOX, seed=5, first_frame=1000, codeword=cw)
+    out = dec.decode(llr)
+    bits = fp.unpack_bits(out["bits"], code.n)
+    errs = (bits[:, info] != cw[info][None, :]).sum(axis=1)
+    assert (sim["iters"] == out["iters"]).all()
+    assert (sim["frame_err"] == errs).all()
+    assert sim["frames"] == frames and sim["bit_errors"] == errs.sum() and sim["frame_errors"] == (errs > 0).sum()
+    assert sim["iter_sum"] == out["iters"].sum()
+    # spot check the decode itself against the oracle
+    orc = po.Oracle(t)
+    for f in range(0, frames, 97):
+        assert orc.decode(llr[f], precheck=precheck)[0] == out["iters"][f]
+    dec.close()
+
+
+def test_shortening_pins(fp, golden):
+    """ArrayLDPC_Debug_Shorten (PerfTest.cpp:410-414): the first short_len info positions are forced to 7*16."""
+    code = fp.codes.array_p47_r5()
+    dec = fp.Decoder(code, precheck=True)
+    info = golden["a5_info_index"].astype(np.int32)
+    snr = 2 * 10 ** (4.5 / 10) * (1978.0 - 976.0) / 2209.0
+    llr = dec.mc_channel(8, snr, stream=fp.STREAM_REFERENCE, seed=123456789, pin_index=info[:36], pin_value=7 * 16)
+    base = dec.mc_channel(8, snr, stream=fp.STREAM_REFERENCE, seed=123456789)
+    assert (llr[:, info[:36]] == 112).all()
+    rest = np.setdiff1d(np.arange(code.n), info[:36])
+    assert (llr[:, rest] == base[:, rest]).all()
+    sim = dec.mc_run(8, snr, stream=fp.STREAM_REFERENCE, seed=123456789, pin_index=info[:36], pin_value=112,
+                     info_index=info, want_iters=True)
+    assert (sim["iters"] == dec.decode(llr)["iters"]).all()
+    dec.close()
