@@ -140,3 +140,15 @@ def test_shortening_pins(fp, golden):
                      info_index=info, want_iters=True)
     assert (sim["iters"] == dec.decode(llr)["iters"]).all()
     dec.close()
+
+
+def test_driver_run_point_reproduces_transcript(fp, golden):
+    """The sharded driver (one rank here) with the reference stream prints the reference's own two lines."""
+    from fixedpointldpc_b200.montecarlo import Shards, gpu_simulator, reference_print, run_point
+    code = fp.codes.wifi_1944_r12()
+    dec = fp.Decoder(code)
+    sim = gpu_simulator(dec, WIFI_SNR_2DB, stream=fp.STREAM_REFERENCE, seed=123456789,
+                        codeword=golden["wifi_codeword"], info_index=golden["wifi_info_index"])
+    res = run_point(sim, Shards(1, 0, 50000), 100)
+    assert reference_print(res, code.n) == "2732 100 393214\n FER: 0.000254314 BER: 3.57401e-06"
+    dec.close()
