@@ -27,7 +27,39 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+FACADE_DIR = os.path.join(CSRC, "facade")
+INCLUDE_DIR = os.path.join(HERE, "..", "include")
+FACADE_VARIANTS = {"wifi": 0, "a5": 1, "a24": 2, "c79": 3}
+
+
+def wrapper_path(variant):
+    return os.path.join(HERE, "ldpc_wrapper_" + variant)
+
+
+def build_facade(force=False):
+    """The reference-compatible console program (PerfTest/Wrapper drivers on the engine), one binary per
+    compile-time code variant like the reference itself."""
+    srcs = [os.path.join(FACADE_DIR, f) for f in ("PerfTest.cpp", "Wrapper.cpp")]
+    deps = srcs + [os.path.join(INCLUDE_DIR, f) for f in ("ArrayLDPCMacro.h", "ArrayLDPC.h", "PerfTest.h", "ldpc_capi.h")] + [LIB]
+    for name, variant in FACADE_VARIANTS.items():
+        out = wrapper_path(name)
+        if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+            continue
+        cmd = ["g++", "-O2", "-std=c++17", "-DLDPC_CODE_VARIANT=%d" % variant, "-I", INCLUDE_DIR, "-o", out] + srcs + \
+              ["-L", HERE, "-lldpc_b200", "-Wl,-rpath,$ORIGIN"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("g++ failed building " + out)
+
+
 def build(force=False, verbose=False):
+    lib = build_lib(force, verbose)
+    build_facade(force)
+    return lib
+
+
+def build_lib(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \

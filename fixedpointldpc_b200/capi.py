@@ -21,7 +21,8 @@ EXPORTS = (
     "ldpc_code_free", "ldpc_code_dims", "ldpc_code_tables", "ldpc_code_rate", "ldpc_code_save",
     "ldpc_decoder_cfg_default", "ldpc_decoder_create", "ldpc_decoder_destroy", "ldpc_decode_batch",
     "ldpc_decode_batch_device", "ldpc_decoder_sync", "ldpc_decoder_get_stats", "ldpc_device_count",
-    "ldpc_mc_run", "ldpc_mc_run_device", "ldpc_mc_channel",
+    "ldpc_mc_run", "ldpc_mc_run_device", "ldpc_mc_channel", "ldpc_hard_decision_batch",
+    "ldpc_gen_load", "ldpc_gen_from_code", "ldpc_gen_save", "ldpc_gen_free", "ldpc_gen_dims", "ldpc_gen_indices", "ldpc_gen_encode",
 )
 STREAM_PHILOX, STREAM_REFERENCE = 1, 2
 
@@ -95,6 +96,16 @@ def load_library():
     L.ldpc_mc_run.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp, vp, C.POINTER(McCounters)]
     L.ldpc_mc_run_device.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp, vp, vp, vp]
     L.ldpc_mc_channel.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp]
+    L.ldpc_hard_decision_batch.argtypes = [vp, vp, C.c_size_t, vp, vp]
+    L.ldpc_gen_load.restype = vp
+    L.ldpc_gen_load.argtypes = [C.c_char_p, ip]
+    L.ldpc_gen_free.argtypes = [vp]
+    L.ldpc_gen_from_code.restype = vp
+    L.ldpc_gen_from_code.argtypes = [vp, vp, C.c_int, ip]
+    L.ldpc_gen_save.argtypes = [vp, C.c_char_p]
+    L.ldpc_gen_dims.argtypes = [vp, ip, ip, ip]
+    L.ldpc_gen_indices.argtypes = [vp, vp, vp]
+    L.ldpc_gen_encode.argtypes = [vp, C.c_char_p, C.c_int, vp]
     _lib = L
     return L
 
@@ -181,6 +192,45 @@ class Code:
             pass
 
 
+class Generator:
+    """Format-B generator equations + FP_Encoder::encode (host side; ArrayLDPC_Encoder.cpp:34-225)."""
+
+    def __init__(self, path=None, code=None, parity_cols=None):
+        """Generator(path) parses Format B; Generator(code=..., parity_cols=...) derives the equations from H by
+        GF(2) elimination (parity_cols fixes the solved-for columns, None = greedy from the last column)."""
+        L = load_library()
+        err = C.c_int()
+        if path is not None:
+            self._h = L.ldpc_gen_load(os.fsencode(path), C.byref(err))
+        else:
+            pc = None if parity_cols is None else np.ascontiguousarray(parity_cols, np.int32)
+            self._h = L.ldpc_gen_from_code(code._h, _ptr(pc), 0 if pc is None else len(pc), C.byref(err))
+        if not self._h:
+            _check(err.value)
+        v = [C.c_int() for _ in range(3)]
+        _check(L.ldpc_gen_dims(self._h, *[C.byref(x) for x in v]))
+        self.n, self.rows, self.k = (x.value for x in v)
+        self.info_index = np.zeros(self.k, np.int32)
+        self.parity_index = np.zeros(self.rows, np.int32)
+        _check(L.ldpc_gen_indices(self._h, _ptr(self.info_index), _ptr(self.parity_index)))
+
+    def save(self, path):
+        _check(load_library().ldpc_gen_save(self._h, os.fsencode(path)))
+
+    def encode(self, info_bytes):
+        cw = np.zeros(self.n, np.uint8)
+        _check(load_library().ldpc_gen_encode(self._h, info_bytes, len(info_bytes), _ptr(cw)))
+        return cw
+
+    def __del__(self):
+        try:
+            if self._h:
+                load_library().ldpc_gen_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 class Decoder:
     """Batched FP_Decoder::decode_general_fp (precheck=False) / decode_fixpoint (precheck=True)."""
 
@@ -218,6 +268,15 @@ class Decoder:
         """Device-pointer call, asynchronous on `stream` (raw cudaStream_t value or None)."""
         _check(load_library().ldpc_decode_batch_device(self._h, llr_ptr, llr_bits, frames, iters_ptr, bits_ptr,
                                                        post_ptr, v2c_ptr, stream))
+
+    def hard_decision(self, values):
+        """FP_Decoder::hardDecision / checkPost_fp*: returns (fail[frames], bits[frames][nw32])."""
+        c = self.code
+        values = np.ascontiguousarray(values, np.int32).reshape(-1, c.n)
+        fail = np.zeros(len(values), np.int32)
+        bits = np.zeros((len(values), c.nw32), np.uint32)
+        _check(load_library().ldpc_hard_decision_batch(self._h, _ptr(values), len(values), _ptr(fail), _ptr(bits)))
+        return fail, bits
 
     def sync(self):
         _check(load_library().ldpc_decoder_sync(self._h))

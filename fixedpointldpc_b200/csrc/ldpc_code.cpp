@@ -211,4 +211,142 @@ int save_format_a(const ldpc_code &c, const char *path)
     return LDPC_OK;
 }
 
+// ---- generator (Format B) ------------------------------------------------------------------
+// Reference: ArrayLDPC_Encoder.cpp:45-83.  Header "n rows", two ignored degree bounds, n column flags
+// (1 = parity / pivot column), `rows` equation lengths, then the equations.
+int load_generator(const char *path, ldpc_gen &out)
+{
+    if (!path) { set_error("NULL path"); return LDPC_ERR_ARG; }
+    std::vector<long> t;
+    set_error("");
+    if (!read_tokens(path, t)) { set_error(std::string("cannot open ") + path); return LDPC_ERR_IO; }
+    if (t.size() < 4) { if (!*last_error()) set_error("generator file too short"); return LDPC_ERR_FORMAT; }
+    const long n = t[0], rows = t[1];
+    if (n <= 0 || rows <= 0 || rows >= n || t.size() < 4 + (size_t)n + (size_t)rows) {
+        set_error("bad generator header"); return LDPC_ERR_FORMAT;
+    }
+    ldpc_gen g;
+    g.n = (int)n; g.rows = (int)rows;
+    size_t pos = 4;
+    g.flag.assign(t.begin() + pos, t.begin() + pos + n); pos += n;
+    for (int v = 0; v < g.n; ++v) (g.flag[v] == 1 ? g.parity_index : g.info_index).push_back(v);
+    if ((int)g.parity_index.size() != g.rows) { set_error("number of flagged columns != number of equations"); return LDPC_ERR_FORMAT; }
+    std::vector<long> deg(t.begin() + pos, t.begin() + pos + rows); pos += rows;
+    long total = 0;
+    for (long d : deg) { if (d < 0) return LDPC_ERR_FORMAT; total += d; }
+    if (t.size() != pos + (size_t)total) { set_error("equation lengths do not match the file size"); return LDPC_ERR_FORMAT; }
+    g.eq.resize(rows);
+    for (long r = 0; r < rows; ++r)
+        for (long j = 0; j < deg[r]; ++j) {
+            long v = t[pos++];
+            if (v < 0 || v >= n) { set_error("equation entry out of range"); return LDPC_ERR_FORMAT; }
+            g.eq[r].push_back((int)v);
+        }
+    out = std::move(g);
+    return LDPC_OK;
+}
+
+// GF(2) Gauss-Jordan elimination on bit-packed rows of H.  The result has one equation per pivot:
+// parity column + the information columns it depends on, i.e. exactly the shape of the reference's
+// Format B rows (every row holds one flagged column).
+int derive_generator(const ldpc_code &code, const int *parity_cols, int nparity, ldpc_gen &out)
+{
+    const int n = code.n, m = code.m, words = (n + 63) / 64;
+    std::vector<std::vector<unsigned long long>> row(m, std::vector<unsigned long long>(words, 0ull));
+    for (int r = 0; r < m; ++r)
+        for (int k = 0; k < code.cdeg[r]; ++k) {
+            int v = code.clist[(size_t)r * code.dc_max + k];
+            row[r][v >> 6] ^= 1ull << (v & 63);
+        }
+    std::vector<int> order;  // candidate pivot columns in the order they are tried
+    if (parity_cols) {
+        for (int i = 0; i < nparity; ++i) {
+            if (parity_cols[i] < 0 || parity_cols[i] >= n) { set_error("parity column out of range"); return LDPC_ERR_ARG; }
+            order.push_back(parity_cols[i]);
+        }
+    } else {
+        for (int v = n - 1; v >= 0; --v) order.push_back(v);
+    }
+    std::vector<int> pivot_col;  // pivot column of row i after elimination (rows 0..rank-1)
+    int rank = 0;
+    for (int col : order) {
+        if (rank == m) break;
+        int sel = -1;
+        for (int r = rank; r < m; ++r)
+            if ((row[r][col >> 6] >> (col & 63)) & 1ull) { sel = r; break; }
+        if (sel < 0) {
+            if (parity_cols) continue;  // dependent within the requested set: tolerated, reported below
+            continue;
+        }
+        std::swap(row[rank], row[sel]);
+        for (int r = 0; r < m; ++r)
+            if (r != rank && ((row[r][col >> 6] >> (col & 63)) & 1ull))
+                for (int w = 0; w < words; ++w) row[r][w] ^= row[rank][w];
+        pivot_col.push_back(col);
+        ++rank;
+    }
+    if (parity_cols) {
+        // the requested columns must explain every independent check
+        for (int r = rank; r < m; ++r)
+            for (int w = 0; w < words; ++w)
+                if (row[r][w]) { set_error("the given parity columns do not span the row space of H"); return LDPC_ERR_ARG; }
+    }
+    ldpc_gen g;
+    g.n = n; g.rows = rank;
+    g.flag.assign(n, 0);
+    for (int c : pivot_col) g.flag[c] = 1;
+    for (int v = 0; v < n; ++v) (g.flag[v] ? g.parity_index : g.info_index).push_back(v);
+    // equation i belongs to the i-th flagged column in ascending order (ArrayLDPC_Encoder.cpp:56-69)
+    std::vector<int> row_of_col(n, -1);
+    for (int i = 0; i < rank; ++i) row_of_col[pivot_col[i]] = i;
+    g.eq.resize(rank);
+    for (int i = 0; i < rank; ++i) {
+        const std::vector<unsigned long long> &bits = row[row_of_col[g.parity_index[i]]];
+        for (int v = 0; v < n; ++v)
+            if ((bits[v >> 6] >> (v & 63)) & 1ull) g.eq[i].push_back(v);
+    }
+    out = std::move(g);
+    return LDPC_OK;
+}
+
+int save_generator(const ldpc_gen &g, const char *path)
+{
+    FILE *f = std::fopen(path, "w");
+    if (!f) { set_error(std::string("cannot write ") + path); return LDPC_ERR_IO; }
+    size_t dmax = 0;
+    for (const auto &e : g.eq) dmax = std::max(dmax, e.size());
+    std::fprintf(f, "%d %d \n%d %d \n", g.n, g.rows, 0, (int)dmax);
+    for (int v = 0; v < g.n; ++v) std::fprintf(f, "%d ", g.flag[v]);
+    std::fprintf(f, "\n");
+    for (const auto &e : g.eq) std::fprintf(f, "%d ", (int)e.size());
+    std::fprintf(f, "\n");
+    for (const auto &e : g.eq) {
+        for (int v : e) std::fprintf(f, "%d ", v);
+        std::fprintf(f, "\n");
+    }
+    std::fclose(f);
+    return LDPC_OK;
+}
+
+// Reference: ArrayLDPC_Encoder.cpp:160-225.
+int encode(const ldpc_gen &g, const char *info, int info_len, uint8_t *codeword)
+{
+    const int k = g.n - g.rows;
+    if (!info || !codeword || info_len < 1 || (info_len - 1) * 8 + k % 8 < k) {
+        set_error("info buffer shorter than k bits"); return LDPC_ERR_ARG;
+    }
+    std::vector<uint8_t> bit((size_t)info_len * 8);
+    int cnt = 0;
+    for (int i = 0; i < info_len - 1; ++i)
+        for (int j = 0; j < 8; ++j) bit[cnt++] = (info[i] >> j) & 1;
+    for (int j = 0; j < k % 8; ++j) bit[cnt++] = (info[info_len - 1] >> j) & 1;
+    for (int i = 0; i < k; ++i) codeword[g.info_index[i]] = bit[i];
+    for (int r = 0; r < g.rows; ++r) {
+        uint8_t par = 0;
+        for (int v : g.eq[r]) if (g.flag[v] == 0) par ^= codeword[v];
+        codeword[g.parity_index[r]] = par;
+    }
+    return LDPC_OK;
+}
+
 }  // namespace ldpc

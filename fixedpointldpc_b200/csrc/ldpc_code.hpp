@@ -19,6 +19,14 @@ struct ldpc_code {
     double rate = 0.0;
 };
 
+// Generator equations in the reference's Format B (members of FP_Encoder, ArrayLDPCMacro.h:191-206)
+struct ldpc_gen {
+    int n = 0, rows = 0;
+    std::vector<int> flag;                 // ColumnFlag[n]
+    std::vector<int> info_index, parity_index;
+    std::vector<std::vector<int>> eq;      // G_mlist rows
+};
+
 namespace ldpc {
 
 void set_error(const std::string &msg);
@@ -30,5 +38,9 @@ int load_file(const char *path, int format, ldpc_code &out);
 int build_array(int p, int nrows, const int *row_mult, int ncols, const int *col_sel, int backward,
                 ldpc_code &out);
 int save_format_a(const ldpc_code &code, const char *path);
+int load_generator(const char *path, ldpc_gen &out);
+int encode(const ldpc_gen &g, const char *info, int info_len, uint8_t *codeword);
+int derive_generator(const ldpc_code &code, const int *parity_cols, int nparity, ldpc_gen &out);
+int save_generator(const ldpc_gen &g, const char *path);
 
 }  // namespace ldpc

@@ -385,6 +385,56 @@ ldpc_code *ldpc_code_array(int p, int nrows, const int *row_mult, int ncols, con
 
 void ldpc_code_free(ldpc_code *code) { delete code; }
 
+ldpc_gen *ldpc_gen_load(const char *path, int *err)
+{
+    ldpc_gen *g = new ldpc_gen;
+    int st = ldpc::load_generator(path, *g);
+    if (err) *err = st;
+    if (st != LDPC_OK) { delete g; return nullptr; }
+    return g;
+}
+
+ldpc_gen *ldpc_gen_from_code(const ldpc_code *code, const int32_t *parity_cols, int nparity, int *err)
+{
+    if (!code) { if (err) *err = LDPC_ERR_ARG; return nullptr; }
+    ldpc_gen *g = new ldpc_gen;
+    int st = ldpc::derive_generator(*code, parity_cols, nparity, *g);
+    if (err) *err = st;
+    if (st != LDPC_OK) { delete g; return nullptr; }
+    return g;
+}
+
+int ldpc_gen_save(const ldpc_gen *g, const char *path)
+{
+    if (!g || !path) return LDPC_ERR_ARG;
+    return ldpc::save_generator(*g, path);
+}
+
+void ldpc_gen_free(ldpc_gen *gen) { delete gen; }
+
+int ldpc_gen_dims(const ldpc_gen *g, int *n, int *rows, int *k)
+{
+    if (!g) return LDPC_ERR_ARG;
+    if (n) *n = g->n;
+    if (rows) *rows = g->rows;
+    if (k) *k = g->n - g->rows;
+    return LDPC_OK;
+}
+
+int ldpc_gen_indices(const ldpc_gen *g, int32_t *info_index, int32_t *parity_index)
+{
+    if (!g) return LDPC_ERR_ARG;
+    if (info_index) std::copy(g->info_index.begin(), g->info_index.end(), info_index);
+    if (parity_index) std::copy(g->parity_index.begin(), g->parity_index.end(), parity_index);
+    return LDPC_OK;
+}
+
+int ldpc_gen_encode(const ldpc_gen *g, const char *info, int info_len, uint8_t *codeword)
+{
+    if (!g) return LDPC_ERR_ARG;
+    return ldpc::encode(*g, info, info_len, codeword);
+}
+
 int ldpc_code_dims(const ldpc_code *c, int *n, int *m, int *edges, int *dc_max, int *dv_max)
 {
     if (!c) return LDPC_ERR_ARG;
@@ -573,6 +623,18 @@ int ldpc_mc_channel(ldpc_decoder *d, const ldpc_mc_cfg *cfg, size_t frames, int3
     CUDA_TRY(cudaMemcpyAsync(llr, d->d_mc_llr, frames * d->code.n * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return LDPC_OK;
+}
+
+int ldpc_hard_decision_batch(ldpc_decoder *d, const int32_t *values, size_t frames, int32_t *fail, uint32_t *bits)
+{
+    if (!d || !values || !fail) { ldpc::set_error("NULL decoder / values / fail"); return LDPC_ERR_ARG; }
+    // zero iterations: the kernel initialises the slot from the values, evaluates the syndrome of their hard
+    // decisions and stops; the iteration output then carries the syndrome flag (see KParams::max_iter)
+    const int saved = d->cfg.max_iter;
+    d->cfg.max_iter = 0;
+    int rc = ldpc_decode_batch(d, values, frames, fail, bits, nullptr, nullptr);
+    d->cfg.max_iter = saved;
+    return rc;
 }
 
 int ldpc_decoder_sync(ldpc_decoder *d)

@@ -39,7 +39,7 @@ struct KParams {
     int n, m, E, dc_max, dv_max;  // E = dc_max*m words per word set (slot-major, holes for short rows)
     // schedule
     int W;         // word sets per CTA
-    int max_iter;  // MAX_ITER
+    int max_iter;  // MAX_ITER; 0 = hard decision + syndrome only (iters output: 0 pass, 1 fail)
     int precheck;  // decode_fixpoint's hardDecision pre-check
     // io
     const void *llr;  // [frames][n] int32 or int16
@@ -332,6 +332,7 @@ struct Ctrl {
     uint32_t fail[MAX_W];   // per word set: lanes with at least one unsatisfied check
     uint32_t keep[MAX_W];   // per word set: lane masks whose c2v take part in the variable phase
     uint32_t gflag[MAX_W];  // per word set: lanes that left the guard range (Packed16)
+    uint32_t failed[MAX_W]; // copy of `fail` from the last bookkeeping step, read by the finish code
     int fid[MAX_SLOTS];     // frame index decoded in the slot, -1 = idle
     int it[MAX_SLOTS];      // iterations completed by that frame
     uint32_t lehmer[MAX_SLOTS];  // Lehmer state before the slot's frame (MC mode 2)
@@ -479,7 +480,8 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
                     const int w = s / T::LANES, lane = s % T::LANES;
                     const int f = ctrl->fid[s];
                     const bool overflow = (ctrl->gflag[w] >> lane) & 1u;
-                    if (tid == 0) p.iters[f] = overflow ? -1 : ctrl->it[s];
+                    if (tid == 0)
+                        p.iters[f] = overflow ? -1 : (p.max_iter == 0 ? (int)((ctrl->failed[w] >> lane) & 1u) : ctrl->it[s]);
                     const uint32_t *ew = edge + (size_t)w * E;
                     const bool count_errors = p.mc_mode != 0 && !overflow;
                     if (p.bits || count_errors) {
@@ -675,7 +677,7 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
             }
             for (int s = 0; s < nslots; ++s)
                 if (ctrl->fid[s] >= 0) ctrl->keep[s / T::LANES] |= T::lane_mask(s % T::LANES);
-            for (int w = 0; w < W; ++w) ctrl->fail[w] = 0u;
+            for (int w = 0; w < W; ++w) { ctrl->failed[w] = ctrl->fail[w]; ctrl->fail[w] = 0u; }
         }
         if (fin) __syncthreads();  // the finish code reads what thread 0 just wrote
     }

@@ -119,6 +119,11 @@ int ldpc_decode_batch_device(ldpc_decoder *dec, const void *d_llr, int llr_bits,
                              int32_t *d_iters, uint32_t *d_bits, int32_t *d_post, int32_t *d_v2c,
                              void *stream);
 
+/* Batched FP_Decoder::hardDecision / checkPost_fp / checkPost_fp_general (ArrayLDPC_Decoder.cpp:270-333,
+ * 375-420) on HOST buffers: bits = (value > 0 ? 0 : 1) and fail[f] = 1 if any check is unsatisfied, else 0.
+ * `values` are channel LLRs (hardDecision) or posteriors (checkPost*). */
+int ldpc_hard_decision_batch(ldpc_decoder *dec, const int32_t *values, size_t frames, int32_t *fail, uint32_t *bits);
+
 /* Blocks until everything queued on the decoder's streams has finished. */
 int ldpc_decoder_sync(ldpc_decoder *dec);
 
@@ -136,6 +141,27 @@ typedef struct {
 } ldpc_decoder_stats;
 
 int ldpc_decoder_get_stats(const ldpc_decoder *dec, ldpc_decoder_stats *out);
+
+/* ------------------------------------------------------------------ generator / encoder (host) */
+
+/* Replaces FP_Encoder::FP_Encoder(char*, int) (ArrayLDPC_Encoder.cpp:34-157): parses Format B
+ * ("n rows / dv dc / ColumnFlag[n] / ChkDeg[rows] / rows lists"), flag 1 = parity column. */
+ldpc_gen *ldpc_gen_load(const char *path, int *err);
+/* Derive generator equations from H by GF(2) elimination (replaces the offline MATLAB tools
+ * codes/simplfy_generator_alist.m, codes/alist_to_binary.m).  parity_cols[nparity] fixes which columns
+ * are solved for (e.g. the flagged columns of an existing Format B file); NULL picks pivots greedily from
+ * the LAST column backwards, so the information bits occupy the leading columns.  rank(H) equations result. */
+ldpc_gen *ldpc_gen_from_code(const ldpc_code *code, const int32_t *parity_cols, int nparity, int *err);
+/* Writes Format B as FP_Encoder reads it. */
+int ldpc_gen_save(const ldpc_gen *gen, const char *path);
+void ldpc_gen_free(ldpc_gen *gen);
+/* n, rows (= parity equations), k = n - rows */
+int ldpc_gen_dims(const ldpc_gen *gen, int *n, int *rows, int *k);
+/* InfoIndex[k] / ParityIndex[rows] (ArrayLDPC_Encoder.cpp:56-69); either may be NULL */
+int ldpc_gen_indices(const ldpc_gen *gen, int32_t *info_index, int32_t *parity_index);
+/* FP_Encoder::encode(char*, int) (ArrayLDPC_Encoder.cpp:160-225): info bytes, LSB first, the last byte
+ * supplies k % 8 bits; codeword[n] receives 0/1. */
+int ldpc_gen_encode(const ldpc_gen *gen, const char *info, int info_len, uint8_t *codeword);
 
 /* ------------------------------------------------------------------ Monte-Carlo mode (device) */
 

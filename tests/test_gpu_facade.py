@@ -1,0 +1,109 @@
+"""The reference-compatible C++ facade (include/ArrayLDPCMacro.h, PerfTest.h) and console program on the GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, tables_of, valid_mask
+
+pytestmark = pytest.mark.gpu
+
+PKG = os.path.join(ROOT, "fixedpointldpc_b200")
+WIFI_MSG = b"OMG  how long   dd   should this string be to make it 243".ljust(122, b"\0")
+
+
+def _dump_case(tmp, fp, golden, name, tags):
+    code = fp.codes.NAMED[name]()
+    t = tables_of(code)
+    code.save(os.path.join(tmp, "H.txt"))
+    llr = np.concatenate([golden[tag + "_llr"].astype(np.int32) for tag in tags])
+    iters = np.concatenate([golden[tag + "_iters"] for tag in tags]).astype(np.int32)
+    bits = np.concatenate([np.unpackbits(golden[tag + "_bits"], axis=1)[:, :code.n] for tag in tags]).astype(np.uint8)
+    post = np.concatenate([golden[tag + "_post"] if tag + "_post" in golden else np.zeros((len(golden[tag + "_iters"]), code.n), np.int32) for tag in tags]).astype(np.int32)
+    edge = np.concatenate([golden[tag + "_edge"].astype(np.int32) if tag + "_edge" in golden else
+                           np.zeros((len(golden[tag + "_iters"]), t.dc_max, t.m), np.int32) for tag in tags])
+    for arr, fname in ((llr, "llr.bin"), (iters, "iters.bin"), (bits, "bits.bin"), (post, "post.bin"), (edge, "edge.bin"),
+                       (t.cdeg.astype(np.int32), "cdeg.bin")):
+        np.ascontiguousarray(arr).tofile(os.path.join(tmp, fname))
+
+
+def _build_check(tmp, variant):
+    exe = os.path.join(tmp, "facade_check")
+    cmd = ["g++", "-O1", "-std=c++17", "-DLDPC_CODE_VARIANT=%d" % variant, "-I", os.path.join(ROOT, "include"), "-o", exe,
+           os.path.join(ROOT, "tests", "facade_check.cpp"), "-L", PKG, "-lldpc_b200", "-Wl,-rpath," + PKG]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+@pytest.mark.parametrize("name,variant,mode,tags", [
+    ("wifi", 0, "general", ["wifi_2dB", "wifi_0p5dB"]),
+    ("a5", 1, "fixpoint", ["a5_4p5dB", "a5_9dB", "a5_2dB", "a5_9dB"]),
+    ("a5", 1, "general", ["a5_4p5dB"]),
+    ("c79", 3, "general", ["c79_4p5dB", "c79_2dB"]),
+])
+def test_fp_decoder_class_frame_by_frame(tmp_path, fp, golden, name, variant, mode, tags):
+    tmp = str(tmp_path)
+    _dump_case(tmp, fp, golden, name, tags)
+    exe = _build_check(tmp, variant)
+    res = subprocess.run([exe, tmp, mode], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "mismatches 0" in res.stdout
+
+
+def _wifi_files(tmp, fp, golden):
+    code = fp.codes.wifi_1944_r12()
+    code.save(os.path.join(tmp, "H_802.11_IndZero.txt"))
+    parity = np.setdiff1d(np.arange(code.n), golden["wifi_info_index"].astype(np.int64)).astype(np.int32)
+    gen = fp.Generator(code=code, parity_cols=parity)
+    assert (gen.encode(WIFI_MSG) == golden["wifi_codeword"]).all()
+    gen.save(os.path.join(tmp, "H_802.11_IndZerog.txt"))
+
+
+def test_console_program_reproduces_wifi_results(tmp_path, fp, golden):
+    """`echo 2 | wrapper` == wifi_results_4_4_2dB_30iter.txt (the reference's only published output)."""
+    tmp = str(tmp_path)
+    _wifi_files(tmp, fp, golden)
+    res = subprocess.run([os.path.join(PKG, "ldpc_wrapper_wifi")], input="2\n", capture_output=True, text=True, cwd=tmp,
+                         timeout=600)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout == "EbNo in dB? SNR is 2 dB\n2732 100 393214\n FER: 0.000254314 BER: 3.57401e-06\n"
+
+
+def test_console_program_array_perftest(tmp_path, fp, golden):
+    """ArrayLDPC_PerfTest(2 dB) -> `3000 100 100`, (6 dB) -> `142 100 100`, and the two output
+    files are created empty like the reference does."""
+    tmp = str(tmp_path)
+    exe = os.path.join(PKG, "ldpc_wrapper_a5")
+    res = subprocess.run([exe, "2", "2", "1", "test.csv"], capture_output=True, text=True, cwd=tmp, timeout=600)
+    assert res.stdout == "3000 100 100\n FER: 1 BER: 0.0135808\n", res.stdout + res.stderr
+    assert os.path.getsize(os.path.join(tmp, "test.csv")) == 0 and os.path.getsize(os.path.join(tmp, "test.csv_log.txt")) == 0
+    res = subprocess.run([exe, "6", "6", "1", "t6.csv"], capture_output=True, text=True, cwd=tmp, timeout=600)
+    assert res.stdout.startswith("142 100 100\n"), res.stdout
+
+
+def test_console_program_array_debug_and_trials(tmp_path, fp, golden):
+    tmp = str(tmp_path)
+    code = fp.codes.array_p47_r5()
+    parity = np.setdiff1d(np.arange(code.n), golden["a5_info_index"].astype(np.int64)).astype(np.int32)
+    fp.Generator(code=code, parity_cols=parity).save(os.path.join(tmp, "G_array_forward.txt"))
+    exe = os.path.join(PKG, "ldpc_wrapper_a5")
+    res = subprocess.run([exe, "debug"], capture_output=True, text=True, cwd=tmp, timeout=900)
+    assert res.returncode == 0, res.stderr
+    lines = res.stdout.strip().split("\n")
+    assert lines[0].startswith("SNR is 4.02")
+    biterr, pckerr, counter = (float(x) for x in lines[1].split())
+    # ArrayLDPC_Debug flow at 4.5 dB: 993 frame errors in the first 20 000 frames -> FER ~ 0.05
+    assert pckerr == 100 and 1500 < counter < 2700 and 20 < biterr / pckerr < 35
+    res = subprocess.run([exe, "decodetrial", "4.5", "20000"], capture_output=True, text=True, cwd=tmp, timeout=900)
+    assert "bits per second for decoder" in res.stdout and "equivalent SNR is: 4.02" in res.stdout
+    res = subprocess.run([exe, "timetrial", "2", "300"], capture_output=True, text=True, cwd=tmp, timeout=900)
+    assert res.stdout.startswith("9000 300 300\n")          # every frame runs 30 iterations at 2 dB
+    res = subprocess.run([exe, "shorten", "36"], capture_output=True, text=True, cwd=tmp, timeout=900)
+    assert res.returncode == 0 and " FER: " in res.stdout
+    res = subprocess.run([exe, "sweep", "4.0", "5.0", "0.5", "sweep.csv", "50"], capture_output=True, text=True, cwd=tmp,
+                         timeout=900)
+    rows = open(os.path.join(tmp, "sweep.csv")).read().strip().split("\n")
+    assert rows[0].startswith("EbN0_dB,frames") and len(rows) == 4
+    fers = [float(r.split(",")[4]) for r in rows[1:]]
+    assert fers[0] > fers[1] > fers[2] > 0
