@@ -29,26 +29,32 @@ typedef void (*kernel_fn)(const KParams);
 struct KernelChoice {
     kernel_fn fn = nullptr;
     int max_threads = 0;
+    int ni = 1;
+    int ctas_per_sm = 1;
 };
 
-template <class T, int DC, bool REG, int DV> static KernelChoice make_choice()
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA> static KernelChoice make_choice()
 {
     KernelChoice k;
-    k.fn = decode_kernel<T, DC, REG, DV>;
-    k.max_threads = LaunchShape<DC>::MAX_THREADS;
+    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA>;
+    k.max_threads = MAXT;
+    k.ni = NI;
+    k.ctas_per_sm = NCTA;
     return k;
 }
 
-// Exact instantiations for the four named codes plus a generic bucket.
+// Exact instantiations for the four named codes plus a generic bucket.  NI = word sets interleaved per thread
+// in the check phase (instruction-level parallelism across independent chains); MAXT bounds the CTA so that the
+// NI forward arrays stay in registers.
 template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
 {
     bool regular = true;
     for (int d : c.cdeg) regular &= (d == c.dc_max);
-    if (regular && c.dc_max == 47 && c.dv_max <= 5) return make_choice<T, 47, true, 5>();    // array p47 r5
-    if (regular && c.dc_max == 47 && c.dv_max <= 24) return make_choice<T, 47, true, 24>();  // array p47 r24
-    if (regular && c.dc_max == 28 && c.dv_max <= 4) return make_choice<T, 28, true, 4>();    // cut79
-    if (c.dc_max <= 8 && c.dv_max <= 12) return make_choice<T, 8, false, 12>();              // 802.11n 1944 r1/2
-    if (c.dc_max <= 64 && c.dv_max <= 32) return make_choice<T, 64, false, 32>();
+    if (regular && c.dc_max == 47 && c.dv_max <= 5) return make_choice<T, 47, true, 5, 2, 256, 2>();     // array p47 r5
+    if (regular && c.dc_max == 47 && c.dv_max <= 24) return make_choice<T, 47, true, 24, 1, 768, 1>();   // array p47 r24
+    if (regular && c.dc_max == 28 && c.dv_max <= 4) return make_choice<T, 28, true, 4, 2, 384, 2>();     // cut79
+    if (c.dc_max <= 8 && c.dv_max <= 12) return make_choice<T, 8, false, 12, 2, 512, 2>();               // 802.11n 1944 r1/2
+    if (c.dc_max <= 64 && c.dv_max <= 32) return make_choice<T, 64, false, 32, 1, 512, 1>();
     return KernelChoice();
 }
 
@@ -97,12 +103,15 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
     if (!k.fn) { set_error("check degree > 64 or variable degree > 32: no kernel instantiation"); return LDPC_ERR_UNSUPPORTED; }
     if ((long long)c.dc_max * c.m > 65535) { set_error("dc_max*m exceeds the 16-bit edge address space"); return LDPC_ERR_UNSUPPORTED; }
     const int per_w = (c.dc_max * c.m + c.n + c.m) * 4;  // messages + channel values + per-check XOR
-    const int budget = d.max_smem - (int)sizeof(Ctrl) - 64;
+    // co-resident CTAs share the SM's shared memory (228 KB minus 1 KB reserved per CTA)
+    const int sm_total = d.max_smem + 1024;
+    const int budget = (k.ctas_per_sm > 1 ? sm_total / k.ctas_per_sm - 1024 : d.max_smem) - (int)sizeof(Ctrl) - 64;
     int W = std::min(budget / per_w, (int)MAX_W);
     if (want_slots > 0) W = std::min(W, std::max(1, (want_slots + lanes - 1) / lanes));
-    if (W < 1) { set_error("one frame's messages do not fit in shared memory"); return LDPC_ERR_UNSUPPORTED; }
+    if (W < k.ni) { set_error("the word sets one thread interleaves do not fit in shared memory"); return LDPC_ERR_UNSUPPORTED; }
+    W -= W % k.ni;  // the check phase walks the word sets in groups of NI
     // CTA size: best check-phase lane efficiency, ties to the larger CTA
-    const int items = W * c.m;
+    const int items = (W / k.ni) * c.m;
     int best_t = 0; double best_e = -1;
     for (int t = 128; t <= k.max_threads; t += 32) {
         int passes = (items + t - 1) / t;
@@ -168,9 +177,11 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     if (frames <= 0) return LDPC_OK;
     const ldpc_code &c = d.code;
     KParams p;
+    std::memset(&p, 0, sizeof p);
     p.cdeg = d.d_cdeg; p.vdeg = d.d_vdeg; p.vedge = d.d_vedge;
     p.n = c.n; p.m = c.m; p.E = c.dc_max * c.m; p.dc_max = c.dc_max; p.dv_max = c.dv_max;
     p.W = pl.W; p.max_iter = d.cfg.max_iter; p.precheck = d.cfg.precheck;
+    p.inv_m = (uint32_t)((1ull << 32) / (unsigned)c.m) + 1u;
     p.llr = llr; p.llr_bits = llr_bits; p.frames = frames;
     p.iters = iters; p.bits = bits; p.nw32 = (c.n + 31) / 32; p.post = post; p.v2c = v2c;
     p.queue = d.d_queue + which;
@@ -184,7 +195,7 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     }
     const int lanes = which == 0 ? 2 : 1;
     const long long slots = (long long)pl.W * lanes;
-    int grid = (int)std::min<long long>(d.sm_count, (frames + slots - 1) / slots);
+    int grid = (int)std::min<long long>((long long)d.sm_count * pl.kernel.ctas_per_sm, (frames + slots - 1) / slots);
     CUDA_TRY(cudaMemsetAsync(p.queue, 0, sizeof(unsigned long long), st));
     pl.kernel.fn<<<grid, pl.threads, pl.smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
@@ -569,6 +580,7 @@ int ldpc_mc_run_device(ldpc_decoder *d, const ldpc_mc_cfg *cfg, size_t frames, u
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
     ldpc::KParams mc;
+    std::memset(&mc, 0, sizeof mc);
     int rc = ldpc::mc_prepare(*d, *cfg, mc, st);
     if (rc != LDPC_OK) return rc;
     if (!d_iters) {  // the fallback list is built from the iteration counts, so they always exist
@@ -609,6 +621,7 @@ int ldpc_mc_channel(ldpc_decoder *d, const ldpc_mc_cfg *cfg, size_t frames, int3
     CUDA_TRY(cudaSetDevice(d->device));
     cudaStream_t st = d->stream;
     ldpc::KParams mc;
+    std::memset(&mc, 0, sizeof mc);
     int rc = ldpc::mc_prepare(*d, *cfg, mc, st);
     if (rc != LDPC_OK) return rc;
     if (d->mc_llr_cap < frames) {

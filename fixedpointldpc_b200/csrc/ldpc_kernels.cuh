@@ -28,6 +28,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace ldpc {
 
@@ -40,6 +41,7 @@ struct KParams {
     // schedule
     int W;         // word sets per CTA
     int max_iter;  // MAX_ITER; 0 = hard decision + syndrome only (iters output: 0 pass, 1 fail)
+    uint32_t inv_m;  // floor(2^32 / m) + 1: i / m == umulhi(i, inv_m) for i < 2^16
     int precheck;  // decode_fixpoint's hardDecision pre-check
     // io
     const void *llr;  // [frames][n] int32 or int16
@@ -81,6 +83,19 @@ __device__ __forceinline__ uint32_t lane_sign_mask(uint32_t x)
     return r;
 }
 
+__device__ __forceinline__ uint32_t or3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xfe;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------
 // lane traits
 // ------------------------------------------------------------------------------------------
@@ -118,15 +133,16 @@ struct Scalar32 {
     __device__ static __forceinline__ Acc acc_init(uint32_t llr) { return Acc{(int)llr}; }
     __device__ static __forceinline__ void acc_sub(Acc &a, uint32_t nc) { a.v -= (int)nc; }
     // posterior word + its hard decision in message position (bit = post <= 0, quirk Q3)
-    __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd)
+    template <int D> __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd)
     {
         hd = ((uint32_t)(a.v - 1) >> 1) & HD;  // sign of post-1, moved to bit 30
         return (uint32_t)a.v;
     }
-    __device__ static __forceinline__ uint32_t v2c_word(uint32_t post, uint32_t nc, uint32_t hd, uint32_t &)
+    // sign | magnitude of post + (-c2v); the caller ORs the hard-decision bit in
+    __device__ static __forceinline__ uint32_t v2c_signmag(uint32_t post, uint32_t nc)
     {
         int v = (int)post + (int)nc;
-        return (uint32_t)abs(v) | ((uint32_t)v & SIGN) | hd;
+        return (uint32_t)abs(v) | ((uint32_t)v & SIGN);
     }
     __device__ static __forceinline__ bool guard_hit(uint32_t) { return false; }
     __device__ static __forceinline__ uint32_t guard_lanes(uint32_t) { return 0u; }
@@ -193,21 +209,21 @@ struct Packed16 {
     // yields |post + (-c2v)| >= CLAMP - (2^13+9) > 2^13, so the message guard below catches it,
     // and CLAMP + 2^13 + 9 < 2^15 keeps the packed add from wrapping.
     static constexpr int CLAMP = 24000;
-    __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd)
+    template <int D> __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd)
     {
-        const int lo = max(min(a.lo, CLAMP), -CLAMP), hi = max(min(a.hi, CLAMP), -CLAMP);
+        int lo = a.lo, hi = a.hi;
+        // D <= 2: |post| <= 2^13-1 + 2*(2^13+9) fits the lane, and a wrapped post + (-c2v) still trips the guard
+        if (D > 2) { lo = max(min(lo, CLAMP), -CLAMP); hi = max(min(hi, CLAMP), -CLAMP); }
         const uint32_t pw = __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
         hd = (__vadd2(pw, 0xffffffffu) >> 1) & HD;  // sign of post-1 per lane, moved to bit 14
         return pw;
     }
-    __device__ static __forceinline__ uint32_t v2c_word(uint32_t post, uint32_t nc, uint32_t hd, uint32_t &guard)
+    __device__ static __forceinline__ uint32_t v2c_signmag(uint32_t post, uint32_t nc)
     {
         uint32_t v = __vadd2(post, nc);
         uint32_t m = lane_sign_mask(v);                  // 0xffff in negative lanes
         uint32_t t = __vadd2(v, m);                      // v-1 there
-        uint32_t ms = t ^ (m & 0x7fff7fffu);             // sign | |v|
-        guard |= ms;
-        return ms | hd;
+        return t ^ (m & 0x7fff7fffu);                    // sign | |v|; magnitude bits 13,14 feed the guard
     }
     __device__ static __forceinline__ bool guard_hit(uint32_t guard) { return (guard & GUARD) != 0u; }
     __device__ static __forceinline__ uint32_t guard_lanes(uint32_t guard)
@@ -330,24 +346,65 @@ constexpr int MAX_SLOTS = 2 * MAX_W;
 
 struct Ctrl {
     uint32_t fail[MAX_W];   // per word set: lanes with at least one unsatisfied check
-    uint32_t keep[MAX_W];   // per word set: lane masks whose c2v take part in the variable phase
+    uint32_t fresh[MAX_W];  // per word set: lanes refilled since the last bookkeeping step (iteration count 0)
     uint32_t gflag[MAX_W];  // per word set: lanes that left the guard range (Packed16)
     uint32_t failed[MAX_W]; // copy of `fail` from the last bookkeeping step, read by the finish code
     int fid[MAX_SLOTS];     // frame index decoded in the slot, -1 = idle
     int it[MAX_SLOTS];      // iterations completed by that frame
     uint32_t lehmer[MAX_SLOTS];  // Lehmer state before the slot's frame (MC mode 2)
     unsigned int errs;      // info-bit errors of the frame being finished (MC mode)
-};
-
-template <int DC> struct LaunchShape {
-    static constexpr int MAX_THREADS = DC <= 32 ? 1024 : (DC <= 48 ? 768 : 512);
+    uint32_t fin[2];        // slots that stop, written in the bookkeeping step; indexed by loop-trip parity
 };
 
 // ------------------------------------------------------------------------------------------
-// check phase for one check node, messages e[k*m], k < d
+// check phase: NI independent check nodes of exact degree D per thread, interleaved instruction
+// by instruction so every thread carries NI dependency chains (the chains are serial by
+// construction -- sxor is not associative -- and one chain per thread leaves the ALU pipe idle).
+// The NI nodes are the same check c in NI consecutive word sets: e[i] = e0 + i*wstride.
 // ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG>
-__device__ __forceinline__ void check_node(uint32_t *e, int m, int d, const uint32_t nacc)
+template <class T, int D, int NI>
+__device__ __forceinline__ void check_nodes(uint32_t *e0, int m, int wstride, const uint32_t *nacc0, int nvalid)
+{
+    uint32_t fwd[NI][D - 1], w0[NI], bwd[NI], nacc[NI];
+    uint32_t *e[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        // word sets past the last one alias the first (loads stay in bounds, stores are predicated off)
+        e[i] = e0 + (i < nvalid ? i * wstride : 0);
+        nacc[i] = nacc0[i < nvalid ? i * m : 0];
+        w0[i] = e[i][0];
+        fwd[i][0] = w0[i] & T::MAG;
+    }
+#pragma unroll
+    for (int k = 1; k < D - 1; ++k)
+#pragma unroll
+        for (int i = 0; i < NI; ++i) fwd[i][k] = T::g(fwd[i][k - 1], e[i][k * m] & T::MAG);
+    // nacc = ~XOR of all incoming words (from the syndrome pass); bit 31/15 of (nacc ^ word_k) is
+    // the inverted sign of the outgoing message of slot k.
+#pragma unroll
+    for (int k = D - 1; k >= 1; --k)
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const uint32_t w = e[i][k * m];
+            const uint32_t mag = w & T::MAG;
+            uint32_t o;
+            if (k == D - 1) {
+                o = fwd[i][D - 2];  // c2v[d-1] = Forward[d-2]
+                bwd[i] = mag;
+            } else {
+                o = T::g(fwd[i][k - 1], bwd[i]);  // c2v[k] = sxor(Forward[k-1], Backward[k+1])
+                bwd[i] = T::g(bwd[i], mag);       // Backward[k]
+            }
+            if (i < nvalid) e[i][k * m] = T::neg_c2v(o, nacc[i] ^ w);
+        }
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+        if (i < nvalid) e[i][0] = T::neg_c2v(bwd[i], nacc[i] ^ w0[i]);  // c2v[0] = Backward[1]
+}
+
+// one check node of run-time degree d <= DC (predicated; only for degrees without an exact body)
+template <class T, int DC>
+__device__ __forceinline__ void check_node_any(uint32_t *e, int m, int d, const uint32_t nacc)
 {
     uint32_t fwd[DC - 1];
     const uint32_t w0 = e[0];
@@ -355,38 +412,95 @@ __device__ __forceinline__ void check_node(uint32_t *e, int m, int d, const uint
     uint32_t last = fwd[0];  // ends as Forward[d-2] without a runtime-indexed read of fwd[]
 #pragma unroll
     for (int k = 1; k < DC - 1; ++k) {
-        if (REG || k < d - 1) {
+        if (k < d - 1) {
             fwd[k] = T::g(fwd[k - 1], e[k * m] & T::MAG);
             last = fwd[k];
         }
     }
-    // nacc = ~XOR of all incoming words (from the syndrome pass); bit 31/15 of (nacc ^ word_k) is
-    // the inverted sign of the outgoing message of slot k.
     uint32_t bwd = 0;
 #pragma unroll
     for (int k = DC - 1; k >= 1; --k) {
-        if (REG || k < d) {
+        if (k < d) {
             uint32_t w = e[k * m];
             uint32_t mag = w & T::MAG;
             uint32_t o;
-            if (REG ? (k == DC - 1) : (k == d - 1)) {
-                o = last;  // c2v[d-1] = Forward[d-2]
+            if (k == d - 1) {
+                o = last;
                 bwd = mag;
             } else {
-                o = T::g(fwd[k - 1], bwd);  // c2v[k] = sxor(Forward[k-1], Backward[k+1])
-                bwd = T::g(bwd, mag);       // Backward[k]
+                o = T::g(fwd[k - 1], bwd);
+                bwd = T::g(bwd, mag);
             }
             e[k * m] = T::neg_c2v(o, nacc ^ w);
         }
     }
-    e[0] = T::neg_c2v(bwd, nacc ^ w0);  // c2v[0] = Backward[1]
+    e[0] = T::neg_c2v(bwd, nacc ^ w0);
+}
+
+// syndrome pass for the same NI word sets: XOR of the D incoming words of the check
+template <int D, int NI>
+__device__ __forceinline__ void check_xors(const uint32_t *e0, int m, int wstride, int nvalid, uint32_t (&acc)[NI])
+{
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const uint32_t *e = e0 + (i < nvalid ? i * wstride : 0);
+        uint32_t a = e[0];
+#pragma unroll
+        for (int k = 1; k + 1 < D; k += 2) a = xor3(a, e[k * m], e[(k + 1) * m]);
+        if ((D - 1) % 2) a ^= e[(D - 1) * m];
+        acc[i] = a;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
-// variable phase for one variable node of exact degree D, all W word sets
-// (ArrayLDPC_Decoder.cpp:121-156: post = LLR + sum c2v, v2c_j = post - c2v_j)
+// variable phase for one variable node of exact degree D (ArrayLDPC_Decoder.cpp:121-156:
+// post = LLR + sum c2v, v2c_j = post - c2v_j), NW word sets at a time for instruction-level
+// parallelism.  POST: also store the posteriors (parity mode).
 // ------------------------------------------------------------------------------------------
-template <class T, int D>
+template <class T, int D, int NW, bool POST>
+__device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, char *base, uint32_t stride,
+                                               const uint32_t (&off)[D], const uint32_t *llr, int v, int w)
+{
+    uint32_t x[NW][D], pw[NW], hd[NW], guard[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        typename T::Acc acc = T::acc_init(llr[(size_t)(w + i) * p.n + v]);
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            x[i][j] = *reinterpret_cast<uint32_t *>(base + i * stride + off[j]);
+            T::acc_sub(acc, x[i][j]);
+        }
+        pw[i] = T::template post_word<D>(acc, hd[i]);
+        guard[i] = 0;
+    }
+#pragma unroll
+    for (int j = 0; j < D; j += 2)
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const uint32_t a = T::v2c_signmag(pw[i], x[i][j]);
+            *reinterpret_cast<uint32_t *>(base + i * stride + off[j]) = a | hd[i];
+            if (j + 1 < D) {
+                const uint32_t b = T::v2c_signmag(pw[i], x[i][j + 1]);
+                *reinterpret_cast<uint32_t *>(base + i * stride + off[j + 1]) = b | hd[i];
+                guard[i] = or3(guard[i], a, b);
+            } else {
+                guard[i] |= a;
+            }
+        }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        if (T::guard_hit(guard[i])) atomicOr(&ctrl->gflag[w + i], T::guard_lanes(guard[i]));
+        if (POST) {
+#pragma unroll
+            for (int lane = 0; lane < T::LANES; ++lane) {
+                const int f = ctrl->fid[(w + i) * T::LANES + lane];
+                if (f >= 0) p.post[(size_t)f * p.n + v] = T::lane_value(pw[i], lane);
+            }
+        }
+    }
+}
+
+template <class T, int D, bool POST>
 __device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr,
                                               int v, int W)
 {
@@ -395,45 +509,27 @@ __device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint
     for (int j = 0; j < D; ++j) off[j] = (uint32_t)p.vedge[(size_t)j * p.n + v] * 4u;
     char *base = reinterpret_cast<char *>(edge);
     const uint32_t stride = (uint32_t)p.E * 4u;
-    for (int w = 0; w < W; ++w, base += stride) {
-        const uint32_t keep = ctrl->keep[w];
-        typename T::Acc acc = T::acc_init(llr[(size_t)w * p.n + v]);
-        uint32_t x[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            x[j] = *reinterpret_cast<uint32_t *>(base + off[j]) & keep;
-            T::acc_sub(acc, x[j]);
-        }
-        uint32_t hd, guard = 0;
-        const uint32_t pw = T::post_word(acc, hd);
-#pragma unroll
-        for (int j = 0; j < D; ++j) *reinterpret_cast<uint32_t *>(base + off[j]) = T::v2c_word(pw, x[j], hd, guard);
-        if (T::guard_hit(guard)) atomicOr(&ctrl->gflag[w], T::guard_lanes(guard));
-        if (p.post) {
-#pragma unroll
-            for (int lane = 0; lane < T::LANES; ++lane) {
-                const int f = ctrl->fid[w * T::LANES + lane];
-                if (f >= 0) p.post[(size_t)f * p.n + v] = T::lane_value(pw, lane);
-            }
-        }
-    }
+    int w = 0;
+    for (; w + 1 < W; w += 2, base += 2 * stride) variable_words<T, D, 2, POST>(p, ctrl, base, stride, off, llr, v, w);
+    if (w < W) variable_words<T, D, 1, POST>(p, ctrl, base, stride, off, llr, v, w);
 }
 
 // any degree (slow path for degrees without an exact instantiation): two passes over the words
 template <class T>
 __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr,
-                                               int v, int W, int dv)
+                                                  int v, int W, int dv)
 {
     for (int w = 0; w < W; ++w) {
         uint32_t *ew = edge + (size_t)w * p.E;
-        const uint32_t keep = ctrl->keep[w];
         typename T::Acc acc = T::acc_init(llr[(size_t)w * p.n + v]);
-        for (int j = 0; j < dv; ++j) T::acc_sub(acc, ew[p.vedge[(size_t)j * p.n + v]] & keep);
+        for (int j = 0; j < dv; ++j) T::acc_sub(acc, ew[p.vedge[(size_t)j * p.n + v]]);
         uint32_t hd, guard = 0;
-        const uint32_t pw = T::post_word(acc, hd);
+        const uint32_t pw = T::template post_word<64>(acc, hd);
         for (int j = 0; j < dv; ++j) {
             uint32_t *q = &ew[p.vedge[(size_t)j * p.n + v]];
-            *q = T::v2c_word(pw, *q & keep, hd, guard);
+            const uint32_t a = T::v2c_signmag(pw, *q);
+            guard |= a;
+            *q = a | hd;
         }
         if (T::guard_hit(guard)) atomicOr(&ctrl->gflag[w], T::guard_lanes(guard));
         if (p.post) {
@@ -445,16 +541,44 @@ __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, 
     }
 }
 
+template <class T, int DV, bool POST>
+__device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr, int W)
+{
+    for (int v = threadIdx.x; v < p.n; v += blockDim.x) {
+        const int dv = p.vdeg[v];
+        bool done = false;
+        if (DV <= 12) {
+            // exact-degree bodies: no per-edge predicates or branches inside
+            switch (dv) {
+#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), POST>(p, ctrl, edge, llr, v, W); done = true; } break;
+                LDPC_VCASE(1) LDPC_VCASE(2) LDPC_VCASE(3) LDPC_VCASE(4) LDPC_VCASE(5) LDPC_VCASE(6)
+                LDPC_VCASE(7) LDPC_VCASE(8) LDPC_VCASE(9) LDPC_VCASE(10) LDPC_VCASE(11) LDPC_VCASE(12)
+#undef LDPC_VCASE
+            default: break;
+            }
+        } else if (dv == DV) {
+            variable_node<T, DV, POST>(p, ctrl, edge, llr, v, W);
+            done = true;
+        }
+        if (!done) variable_node_any<T>(p, ctrl, edge, llr, v, W, dv);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
+//   DC   largest check degree, REG: every check has degree DC
+//   DV   largest variable degree with an exact body
+//   NI   word sets per thread in the check / syndrome phases (W is a multiple of NI)
+//   MAXT, NCTA  launch bounds: CTA size and co-resident CTAs per SM.  Two CTAs drift out of phase, so
+//        one's latency-bound variable phase overlaps the other's ALU-bound check phase.
 // ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG, int DV>
-__global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel(const KParams p)
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA>
+__global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
     const int n = p.n, m = p.m, E = p.E, W = p.W;
-    uint32_t *edge = smem;                // [W][E]
+    uint32_t *edge = smem;                 // [W][E]
     uint32_t *llr = edge + (size_t)W * E;  // [W][n]
     uint32_t *cxor = llr + (size_t)W * n;  // [W][m] inverted XOR of every check's incoming words
     Ctrl *ctrl = reinterpret_cast<Ctrl *>(cxor + (size_t)W * m);
@@ -462,13 +586,21 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
     const long long frames = p.count ? (long long)*p.count : p.frames;
 
     for (int i = tid; i < W * (E + n + m); i += nthreads) smem[i] = 0u;
-    if (tid < MAX_W) { ctrl->fail[tid] = 0u; ctrl->keep[tid] = 0u; ctrl->gflag[tid] = 0u; }
+    if (tid < MAX_W) { ctrl->fail[tid] = 0u; ctrl->fresh[tid] = 0u; ctrl->gflag[tid] = 0u; ctrl->failed[tid] = 0u; }
     if (tid < MAX_SLOTS) { ctrl->fid[tid] = -1; ctrl->it[tid] = 0; }
+    if (tid < 2) ctrl->fin[tid] = 0u;
     __syncthreads();
+    unsigned int trip = 0;
 
     uint32_t fin = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);  // slots to (re)fill
     bool first = true;
-    const int items = W * m;
+    const int items = (W / NI) * m;  // (word-set group, check)
+#ifdef LDPC_PHASE_TIMING
+    long long t_phase[5] = {0, 0, 0, 0, 0}, t_mark = clock64();
+#define LDPC_MARK(k) do { long long t_now = clock64(); t_phase[k] += t_now - t_mark; t_mark = t_now; } while (0)
+#else
+#define LDPC_MARK(k) do { } while (0)
+#endif
 
     for (;;) {
         // ---------------------------------------------------------------- finish + refill
@@ -538,7 +670,7 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
                         ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed,
                                                      lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)ctrl->fid[s]));
                     ctrl->it[s] = 0;
-                    ctrl->keep[w] &= ~T::lane_mask(lane);  // fresh: the next variable phase sees c2v == 0
+                    ctrl->fresh[w] |= 1u << lane;
                     ctrl->gflag[w] &= ~(1u << lane);
                 }
             }
@@ -547,6 +679,14 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
                 if (!((fin >> s) & 1u)) continue;
                 const int w = s / T::LANES, lane = s % T::LANES;
                 const int f = ctrl->fid[s];
+                // a new frame starts from all-zero messages: the check phase maps zeros to zeros and the variable
+                // phase then produces post = LLR, v2c = LLR, which is the reference's initialisation (:45-61)
+                if (T::LANES == 1) {
+                    if (!first) for (int i = tid; i < E; i += nthreads) edge[(size_t)w * E + i] = 0u;
+                } else {
+                    const uint32_t keep = ~T::lane_mask(lane);
+                    if (!first) for (int i = tid; i < E; i += nthreads) edge[(size_t)w * E + i] &= keep;
+                }
                 bool any_bad = false;
                 if (p.mc_mode == 1 && f >= 0) {
                     const unsigned long long g = p.mc_first + (unsigned long long)f;
@@ -596,91 +736,116 @@ __global__ void __launch_bounds__(LaunchShape<DC>::MAX_THREADS, 1) decode_kernel
             if (active == 0) break;
             first = false;
         }
+        LDPC_MARK(0);
 
         // ---------------------------------------------------------------- check phase
-        // (a freshly refilled lane runs it on stale words; its c2v are masked off below)
         for (int i = tid; i < items; i += nthreads) {
-            const int w = i / m, c = i - w * m;
-            check_node<T, DC, REG>(edge + (size_t)w * E + c, m, REG ? DC : (int)p.cdeg[c], cxor[i]);
+            const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
+            uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
+            const uint32_t *nacc0 = cxor + (size_t)(wg * NI) * m + c;
+            if (REG) {
+                check_nodes<T, DC, NI>(e0, m, E, nacc0, NI);
+            } else {
+                const int d = p.cdeg[c];
+                bool done = false;
+                if (DC <= 16) {
+                    switch (d) {
+#define LDPC_CCASE(D) case D: if (D <= DC) { check_nodes<T, (D <= DC ? D : 2), NI>(e0, m, E, nacc0, NI); done = true; } break;
+                        LDPC_CCASE(2) LDPC_CCASE(3) LDPC_CCASE(4) LDPC_CCASE(5) LDPC_CCASE(6) LDPC_CCASE(7) LDPC_CCASE(8)
+                        LDPC_CCASE(9) LDPC_CCASE(10) LDPC_CCASE(11) LDPC_CCASE(12) LDPC_CCASE(13) LDPC_CCASE(14)
+                        LDPC_CCASE(15) LDPC_CCASE(16)
+#undef LDPC_CCASE
+                    default: break;
+                    }
+                }
+                if (!done)
+                    for (int j = 0; j < NI; ++j) check_node_any<T, DC>(e0 + (size_t)j * E, m, d, nacc0[j * m]);
+            }
         }
         __syncthreads();
+        LDPC_MARK(1);
 
         // ---------------------------------------------------------------- variable phase
-        for (int v = tid; v < n; v += nthreads) {
-            const int dv = p.vdeg[v];
-            bool done = false;
-            if (DV <= 12) {
-                // exact-degree bodies: no per-edge predicates or branches inside
-                switch (dv) {
-#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1)>(p, ctrl, edge, llr, v, W); done = true; } break;
-                    LDPC_VCASE(1) LDPC_VCASE(2) LDPC_VCASE(3) LDPC_VCASE(4) LDPC_VCASE(5) LDPC_VCASE(6)
-                    LDPC_VCASE(7) LDPC_VCASE(8) LDPC_VCASE(9) LDPC_VCASE(10) LDPC_VCASE(11) LDPC_VCASE(12)
-#undef LDPC_VCASE
-                default: break;
-                }
-            } else if (dv == DV) {
-                variable_node<T, DV>(p, ctrl, edge, llr, v, W);
-                done = true;
-            }
-            if (!done) variable_node_any<T>(p, ctrl, edge, llr, v, W, dv);
-        }
+        if (p.post) variable_phase<T, DV, true>(p, ctrl, edge, llr, W);
+        else variable_phase<T, DV, false>(p, ctrl, edge, llr, W);
         __syncthreads();
+        LDPC_MARK(2);
 
         // ---------------------------------------------------------------- syndrome pass
         for (int i0 = tid - lane_id; i0 < items; i0 += nthreads) {
             const int i = i0 + lane_id;
             const bool valid = i < items;
-            int w = 0;
-            uint32_t fb = 0;
-            if (valid) {
-                w = i / m;
-                const int c = i - w * m;
-                const uint32_t *e = edge + (size_t)w * E + c;
-                const int d = REG ? DC : (int)p.cdeg[c];
-                uint32_t acc = 0;
+            int wg = 0;
+            uint32_t fb[NI];
 #pragma unroll
-                for (int k = 0; k < DC; ++k)
-                    if (REG || k < d) acc ^= e[k * m];
-                cxor[i] = ~acc;
-                fb = T::fail_bits(acc);
+            for (int j = 0; j < NI; ++j) fb[j] = 0u;
+            if (valid) {
+                wg = (int)__umulhi((uint32_t)i, p.inv_m);
+                const int c = i - wg * m;
+                const uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
+                uint32_t acc[NI];
+                if (REG) {
+                    check_xors<DC, NI>(e0, m, E, NI, acc);
+                } else {
+                    const int d = p.cdeg[c];
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) {
+                        uint32_t a = 0;
+#pragma unroll
+                        for (int k = 0; k < DC; ++k)
+                            if (k < d) a ^= e0[(size_t)j * E + k * m];
+                        acc[j] = a;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    cxor[(size_t)(wg * NI + j) * m + c] = ~acc[j];
+                    fb[j] = T::fail_bits(acc[j]);
+                }
             }
-            const int w0 = __shfl_sync(0xffffffffu, w, 0);
-            // a warp covers at most two word sets when m >= 32; anything else goes the slow way
-            const uint32_t r0 = __reduce_or_sync(0xffffffffu, (valid && w == w0) ? fb : 0u);
-            const uint32_t r1 = __reduce_or_sync(0xffffffffu, (valid && w == w0 + 1) ? fb : 0u);
-            if (lane_id == 0) {
-                if (r0) atomicOr(&ctrl->fail[w0], r0);
-                if (r1) atomicOr(&ctrl->fail[w0 + 1], r1);
+            const int g0 = __shfl_sync(0xffffffffu, wg, 0);
+            // a warp covers at most two word-set groups when m >= 32; anything else goes the slow way
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                const uint32_t r0 = __reduce_or_sync(0xffffffffu, (valid && wg == g0) ? fb[j] : 0u);
+                const uint32_t r1 = __reduce_or_sync(0xffffffffu, (valid && wg == g0 + 1) ? fb[j] : 0u);
+                if (lane_id == 0) {
+                    if (r0) atomicOr(&ctrl->fail[g0 * NI + j], r0);
+                    if (r1) atomicOr(&ctrl->fail[(g0 + 1) * NI + j], r1);
+                }
+                if (valid && wg > g0 + 1 && fb[j]) atomicOr(&ctrl->fail[wg * NI + j], fb[j]);
             }
-            if (valid && w > w0 + 1 && fb) atomicOr(&ctrl->fail[w], fb);
         }
         __syncthreads();
+        LDPC_MARK(3);
 
         // ---------------------------------------------------------------- bookkeeping
-        // Every thread derives the same stop mask; thread 0 then commits the counters.
-        fin = 0;
-        for (int s = 0; s < nslots; ++s) {
-            const int w = s / T::LANES, lane = s % T::LANES;
-            const bool fresh = (ctrl->keep[w] & T::lane_mask(lane)) == 0u;
-            const int it = ctrl->it[s] + (fresh ? 0 : 1);
-            const bool pass = !((ctrl->fail[w] >> lane) & 1u);
-            const bool over = (ctrl->gflag[w] >> lane) & 1u;
-            const bool stop = it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over;
-            if (ctrl->fid[s] >= 0 && stop) fin |= 1u << s;
+        // one thread per slot decides; the stop mask travels through shared memory (double buffered by trip
+        // parity so it can be cleared without another barrier)
+        if (tid < nslots) {
+            const int s = tid, w = s / T::LANES, lane = s % T::LANES;
+            if (ctrl->fid[s] >= 0) {
+                const bool fresh = (ctrl->fresh[w] >> lane) & 1u;
+                const int it = ctrl->it[s] + (fresh ? 0 : 1);
+                const bool pass = !((ctrl->fail[w] >> lane) & 1u);
+                const bool over = (ctrl->gflag[w] >> lane) & 1u;
+                ctrl->it[s] = it;
+                if (it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over) atomicOr(&ctrl->fin[trip & 1], 1u << s);
+            }
         }
         __syncthreads();
-        if (tid == 0) {
-            for (int s = 0; s < nslots; ++s) {
-                if (ctrl->fid[s] < 0) continue;
-                const bool fresh = (ctrl->keep[s / T::LANES] & T::lane_mask(s % T::LANES)) == 0u;
-                ctrl->it[s] += fresh ? 0 : 1;
-            }
-            for (int s = 0; s < nslots; ++s)
-                if (ctrl->fid[s] >= 0) ctrl->keep[s / T::LANES] |= T::lane_mask(s % T::LANES);
-            for (int w = 0; w < W; ++w) { ctrl->failed[w] = ctrl->fail[w]; ctrl->fail[w] = 0u; }
-        }
-        if (fin) __syncthreads();  // the finish code reads what thread 0 just wrote
+        fin = ctrl->fin[trip & 1];
+        if (tid < W) { ctrl->failed[tid] = ctrl->fail[tid]; ctrl->fail[tid] = 0u; ctrl->fresh[tid] = 0u; }
+        if (tid == 0) ctrl->fin[(trip + 1) & 1] = 0u;
+        ++trip;
+        if (fin) __syncthreads();  // the finish code reads what the threads above just wrote
+        LDPC_MARK(4);
     }
+#ifdef LDPC_PHASE_TIMING
+    if (tid == 0 && blockIdx.x == 0)
+        printf("phase cycles (CTA 0): refill %lld check %lld variable %lld syndrome %lld bookkeeping %lld\n", t_phase[0],
+               t_phase[1], t_phase[2], t_phase[3], t_phase[4]);
+#endif
 }
 
 }  // namespace ldpc
