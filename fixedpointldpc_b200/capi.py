@@ -22,7 +22,7 @@ EXPORTS = (
     "ldpc_decoder_cfg_default", "ldpc_decoder_create", "ldpc_decoder_destroy", "ldpc_decode_batch",
     "ldpc_decode_batch_device", "ldpc_decoder_sync", "ldpc_decoder_get_stats", "ldpc_device_count",
     "ldpc_mc_run", "ldpc_mc_run_device", "ldpc_mc_channel", "ldpc_hard_decision_batch",
-    "ldpc_gen_load", "ldpc_gen_from_code", "ldpc_gen_save", "ldpc_gen_free", "ldpc_gen_dims", "ldpc_gen_indices", "ldpc_gen_encode",
+    "ldpc_encode_batch", "ldpc_encode_batch_device", "ldpc_gen_load", "ldpc_gen_from_code", "ldpc_gen_save", "ldpc_gen_free", "ldpc_gen_dims", "ldpc_gen_indices", "ldpc_gen_encode",
 )
 STREAM_PHILOX, STREAM_REFERENCE = 1, 2
 
@@ -47,7 +47,8 @@ class DecoderStats(C.Structure):
 
 class McCfg(C.Structure):
     _fields_ = [("snr", C.c_double), ("sigma", C.c_double), ("stream", C.c_int), ("seed", C.c_uint64),
-                ("first_frame", C.c_uint64), ("codeword", C.c_void_p), ("info_index", C.c_void_p),
+                ("first_frame", C.c_uint64), ("codeword", C.c_void_p), ("d_codewords", C.c_void_p),
+                ("info_index", C.c_void_p),
                 ("info_count", C.c_int), ("pin_index", C.c_void_p), ("pin_count", C.c_int), ("pin_value", C.c_int)]
 
 
@@ -106,6 +107,8 @@ def load_library():
     L.ldpc_gen_dims.argtypes = [vp, ip, ip, ip]
     L.ldpc_gen_indices.argtypes = [vp, vp, vp]
     L.ldpc_gen_encode.argtypes = [vp, C.c_char_p, C.c_int, vp]
+    L.ldpc_encode_batch.argtypes = [vp, C.c_int, vp, C.c_size_t, vp]
+    L.ldpc_encode_batch_device.argtypes = [vp, C.c_int, vp, C.c_size_t, vp, vp]
     _lib = L
     return L
 
@@ -217,6 +220,16 @@ class Generator:
     def save(self, path):
         _check(load_library().ldpc_gen_save(self._h, os.fsencode(path)))
 
+    def encode_batch(self, info_bytes, device=0):
+        """GPU encoder: info_bytes uint8 [frames][ceil(k/8)] (LSB first) -> packed codewords uint32 [frames][nw32]."""
+        info = np.ascontiguousarray(info_bytes, np.uint8).reshape(-1, (self.k + 7) // 8)
+        out = np.zeros((len(info), (self.n + 31) // 32), np.uint32)
+        _check(load_library().ldpc_encode_batch(self._h, device, _ptr(info), len(info), _ptr(out)))
+        return out
+
+    def encode_batch_device(self, info_words_ptr, frames, codewords_ptr, device=0, cuda_stream=None):
+        _check(load_library().ldpc_encode_batch_device(self._h, device, info_words_ptr, frames, codewords_ptr, cuda_stream))
+
     def encode(self, info_bytes):
         cw = np.zeros(self.n, np.uint8)
         _check(load_library().ldpc_gen_encode(self._h, info_bytes, len(info_bytes), _ptr(cw)))
@@ -283,12 +296,14 @@ class Decoder:
 
     # ---- Monte-Carlo mode -------------------------------------------------------------------
     def _mc_cfg(self, snr, sigma=None, stream=STREAM_PHILOX, seed=1, first_frame=0, codeword=None, info_index=None,
-                pin_index=None, pin_value=0):
+                pin_index=None, pin_value=0, d_codewords=None):
         keep = []
         cfg = McCfg()
         cfg.snr = snr
         cfg.sigma = float(np.sqrt(1.0 / snr)) if sigma is None else sigma
         cfg.stream, cfg.seed, cfg.first_frame = stream, seed, first_frame
+        if d_codewords is not None:
+            cfg.d_codewords = d_codewords
         if codeword is not None:
             cw = np.ascontiguousarray(codeword, np.uint8); keep.append(cw); cfg.codeword = cw.ctypes.data
         if info_index is not None:

@@ -20,8 +20,10 @@ struct ldpc_code {
 };
 
 // Generator equations in the reference's Format B (members of FP_Encoder, ArrayLDPCMacro.h:191-206)
+struct ldpc_gen_device;  // device tables of the batched encoder (ldpc_encode.cu), created on first use
 struct ldpc_gen {
     int n = 0, rows = 0;
+    ldpc_gen_device *dev = nullptr;
     std::vector<int> flag;                 // ColumnFlag[n]
     std::vector<int> info_index, parity_index;
     std::vector<std::vector<int>> eq;      // G_mlist rows

@@ -189,7 +189,7 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     p.mc_mode = 0;
     if (mc) {
         p.mc_mode = mc->mc_mode; p.mc_first = mc->mc_first; p.mc_seed = mc->mc_seed; p.mc_gain = mc->mc_gain;
-        p.mc_sigma = mc->mc_sigma; p.mc_cw = mc->mc_cw; p.mc_info = mc->mc_info; p.mc_pin = mc->mc_pin;
+        p.mc_sigma = mc->mc_sigma; p.mc_cw = mc->mc_cw; p.mc_cw_stride = mc->mc_cw_stride; p.mc_info = mc->mc_info; p.mc_pin = mc->mc_pin;
         p.mc_pin_count = mc->mc_pin_count; p.mc_pin_value = mc->mc_pin_value; p.mc_pow = mc->mc_pow;
         p.mc_jump = mc->mc_jump; p.mc_frame_err = mc->mc_frame_err; p.mc_counters = mc->mc_counters;
     }
@@ -242,12 +242,12 @@ __global__ void channel_kernel(const KParams p, int *out)
                 float z[4];
                 philox_normals(p, g, (uint32_t)q, z);
                 for (int h = 0; h < 4; ++h)
-                    if (4 * q + h < p.n) row[4 * q + h] = quantise_llr(p, (double)z[h], cw_bit(p, 4 * q + h));
+                    if (4 * q + h < p.n) row[4 * q + h] = quantise_llr(p, (double)z[h], cw_bit(p, f, 4 * q + h));
             }
         } else {
             const uint32_t state = lehmer_mul((uint32_t)p.mc_seed, lehmer_pow(p.mc_jump, g));
             for (int v = threadIdx.x; v < p.n; v += blockDim.x)
-                row[v] = quantise_llr(p, lehmer_normal(lehmer_mul(state, p.mc_pow[v])), cw_bit(p, v));
+                row[v] = quantise_llr(p, lehmer_normal(lehmer_mul(state, p.mc_pow[v])), cw_bit(p, f, v));
         }
         __syncthreads();
         for (int i = threadIdx.x; i < p.mc_pin_count; i += blockDim.x) row[p.mc_pin[i]] = p.mc_pin_value;
@@ -302,7 +302,8 @@ static int mc_prepare(ldpc_decoder &d, const ldpc_mc_cfg &cfg, KParams &mc, cuda
     CUDA_TRY(cudaStreamSynchronize(st));  // the staging vectors above go out of scope
     mc.mc_mode = cfg.stream; mc.mc_first = cfg.first_frame; mc.mc_seed = cfg.seed;
     mc.mc_gain = 2 * cfg.snr; mc.mc_sigma = cfg.sigma;
-    mc.mc_cw = cfg.codeword ? d.d_mc_cw : nullptr; mc.mc_info = d.d_mc_info;
+    mc.mc_cw = cfg.codeword ? d.d_mc_cw : nullptr; mc.mc_cw_stride = 0; mc.mc_info = d.d_mc_info;
+    if (cfg.d_codewords) { mc.mc_cw = cfg.d_codewords; mc.mc_cw_stride = nw32; }
     mc.mc_pin = d.d_mc_pin; mc.mc_pin_count = cfg.pin_count > 0 ? cfg.pin_count : 0; mc.mc_pin_value = cfg.pin_value;
     mc.mc_pow = d.d_mc_pow; mc.mc_jump = d.mc_jump;
     mc.mc_frame_err = nullptr; mc.mc_counters = d.d_mc_counters;
@@ -421,7 +422,12 @@ int ldpc_gen_save(const ldpc_gen *g, const char *path)
     return ldpc::save_generator(*g, path);
 }
 
-void ldpc_gen_free(ldpc_gen *gen) { delete gen; }
+void ldpc_gen_release_device(ldpc_gen *gen);
+void ldpc_gen_free(ldpc_gen *gen)
+{
+    ldpc_gen_release_device(gen);
+    delete gen;
+}
 
 int ldpc_gen_dims(const ldpc_gen *g, int *n, int *rows, int *k)
 {

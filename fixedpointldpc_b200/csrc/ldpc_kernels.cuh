@@ -65,6 +65,7 @@ struct KParams {
     double mc_gain;                // 2*snr   (LLR = 2*snr*(1 - 2c + N(0,sigma)), PerfTest.cpp:112)
     double mc_sigma;
     const uint32_t *mc_cw;         // [nw32] transmitted codeword bits or NULL (all-zero codeword)
+    int mc_cw_stride;              // 0: one codeword for all frames; nw32: frame f sends mc_cw + f*stride
     const uint32_t *mc_info;       // [nw32] positions calculateBER counts (ArrayLDPC_Decoder.cpp:707-722)
     const int *mc_pin;             // shortening: LLR_fp[pin[i]] = pin_value (PerfTest.cpp:410-414)
     int mc_pin_count, mc_pin_value;
@@ -333,9 +334,9 @@ __device__ __forceinline__ void philox_normals(const KParams &p, unsigned long l
     }
 }
 
-__device__ __forceinline__ uint32_t cw_bit(const KParams &p, int v)
+__device__ __forceinline__ uint32_t cw_bit(const KParams &p, long long f, int v)
 {
-    return p.mc_cw ? (p.mc_cw[v >> 5] >> (v & 31)) & 1u : 0u;
+    return p.mc_cw ? (p.mc_cw[(size_t)f * p.mc_cw_stride + (v >> 5)] >> (v & 31)) & 1u : 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -629,7 +630,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
                             if (lane_id == 0 && v < n) {
                                 if (p.bits) p.bits[(size_t)f * p.nw32 + (v >> 5)] = word;
                                 if (count_errors) {
-                                    const uint32_t sent = p.mc_cw ? p.mc_cw[v >> 5] : 0u;
+                                    const uint32_t sent = p.mc_cw ? p.mc_cw[(size_t)f * p.mc_cw_stride + (v >> 5)] : 0u;
                                     const uint32_t mask = p.mc_info ? p.mc_info[v >> 5] : 0xffffffffu;
                                     errs += __popc((word ^ sent) & mask);
                                 }
@@ -699,7 +700,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
                             if (v < n) {
                                 bool bad;
                                 uint32_t *dst = &llr[(size_t)w * n + v];
-                                *dst = T::set_lane(*dst, lane, quantise_llr(p, (double)z[h], cw_bit(p, v)), bad);
+                                *dst = T::set_lane(*dst, lane, quantise_llr(p, (double)z[h], cw_bit(p, f, v)), bad);
                                 any_bad |= bad;
                             }
                         }
@@ -709,7 +710,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
                         int val = 0;
                         if (f >= 0) {
                             if (p.mc_mode == 2)
-                                val = quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], p.mc_pow[v])), cw_bit(p, v));
+                                val = quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], p.mc_pow[v])), cw_bit(p, f, v));
                             else
                                 val = p.llr_bits == 16 ? (int)reinterpret_cast<const int16_t *>(p.llr)[(size_t)f * n + v]
                                                        : reinterpret_cast<const int *>(p.llr)[(size_t)f * n + v];

@@ -163,6 +163,15 @@ int ldpc_gen_indices(const ldpc_gen *gen, int32_t *info_index, int32_t *parity_i
  * supplies k % 8 bits; codeword[n] receives 0/1. */
 int ldpc_gen_encode(const ldpc_gen *gen, const char *info, int info_len, uint8_t *codeword);
 
+/* Batched GPU encoder: parity_i = popcount(G_i & info) & 1 on bit-packed rows (the reference encodes one
+ * message at a time on the host, ArrayLDPC_Encoder.cpp:199-210).
+ *   info       [frames][ceil(k/8)] message bytes, LSB first like FP_Encoder::encode (:171-183)
+ *   codewords  [frames][ceil(n/32)] packed codeword bits, bit v%32 of word v/32 */
+int ldpc_encode_batch(ldpc_gen *gen, int device, const uint8_t *info, size_t frames, uint32_t *codewords);
+/* Device buffers: d_info [frames][ceil(k/32)] packed message words, d_codewords as above; asynchronous. */
+int ldpc_encode_batch_device(ldpc_gen *gen, int device, const uint32_t *d_info, size_t frames, uint32_t *d_codewords,
+                             void *stream);
+
 /* ------------------------------------------------------------------ Monte-Carlo mode (device) */
 
 /* Noise streams. */
@@ -183,6 +192,8 @@ typedef struct {
     uint64_t seed;             /* Philox key, or the Lehmer state before global frame 0 (rngs.cpp:45: 123456789) */
     uint64_t first_frame;      /* global index of the first frame of this call (frames are independent)  */
     const uint8_t *codeword;   /* [n] transmitted bits, NULL = all-zero codeword                         */
+    const uint32_t *d_codewords; /* DEVICE pointer, [frames][ceil(n/32)] packed: frame f sends row f (e.g. the output of
+                                  ldpc_encode_batch_device for random messages); overrides `codeword` when set   */
     const int32_t *info_index; /* [info_count] positions calculateBER compares (ArrayLDPC_Decoder.cpp:707-722),
                                   NULL = all n positions                                                  */
     int info_count;
