@@ -42,6 +42,8 @@ struct KParams {
     int W;         // word sets per CTA
     int max_iter;  // MAX_ITER; 0 = hard decision + syndrome only (iters output: 0 pass, 1 fail)
     uint32_t inv_m;  // floor(2^32 / m) + 1: i / m == umulhi(i, inv_m) for i < 2^16
+    int stagger;     // cycles the second CTA of every SM waits before its first trip (phase offset)
+    int stagger_from;  // first blockIdx.x that waits
     int precheck;  // decode_fixpoint's hardDecision pre-check
     // io
     const void *llr;  // [frames][n] int32 or int16
@@ -343,6 +345,7 @@ __device__ __forceinline__ uint32_t cw_bit(const KParams &p, long long f, int v)
 // control block in shared memory (after the message and channel words)
 // ------------------------------------------------------------------------------------------
 constexpr int MAX_W = 16;         // word sets per CTA
+constexpr bool PREFETCH_VEDGE = true;   // software-prefetch the next variable's edge addresses (costs registers)
 constexpr int MAX_SLOTS = 2 * MAX_W;
 
 struct Ctrl {
@@ -460,12 +463,12 @@ __device__ __forceinline__ void check_xors(const uint32_t *e0, int m, int wstrid
 // ------------------------------------------------------------------------------------------
 template <class T, int D, int NW, bool POST>
 __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, char *base, uint32_t stride,
-                                               const uint32_t (&off)[D], const uint32_t *llr, int v, int w)
+                                               const uint32_t (&off)[D], const uint32_t *llr, int v, int w, int n)
 {
     uint32_t x[NW][D], pw[NW], hd[NW], guard[NW];
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
-        typename T::Acc acc = T::acc_init(llr[(size_t)(w + i) * p.n + v]);
+        typename T::Acc acc = T::acc_init(llr[(w + i) * n + v]);
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             x[i][j] = *reinterpret_cast<uint32_t *>(base + i * stride + off[j]);
@@ -495,7 +498,7 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, cha
 #pragma unroll
             for (int lane = 0; lane < T::LANES; ++lane) {
                 const int f = ctrl->fid[(w + i) * T::LANES + lane];
-                if (f >= 0) p.post[(size_t)f * p.n + v] = T::lane_value(pw[i], lane);
+                if (f >= 0) p.post[(size_t)f * n + v] = T::lane_value(pw[i], lane);
             }
         }
     }
@@ -503,31 +506,38 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, cha
 
 template <class T, int D, bool POST>
 __device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr,
-                                              int v, int W)
+                                              int v, int W, int n, int E, const uint32_t (&off)[D])
+{
+    char *base = reinterpret_cast<char *>(edge);
+    const uint32_t stride = (uint32_t)E * 4u;
+    int w = 0;
+    for (; w + 1 < W; w += 2, base += 2 * stride) variable_words<T, D, 2, POST>(p, ctrl, base, stride, off, llr, v, w, n);
+    if (w < W) variable_words<T, D, 1, POST>(p, ctrl, base, stride, off, llr, v, w, n);
+}
+
+template <class T, int D, bool POST>
+__device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr,
+                                              int v, int W, int n, int E)
 {
     uint32_t off[D];  // byte offsets of the D edge words inside a word set
 #pragma unroll
-    for (int j = 0; j < D; ++j) off[j] = (uint32_t)p.vedge[(size_t)j * p.n + v] * 4u;
-    char *base = reinterpret_cast<char *>(edge);
-    const uint32_t stride = (uint32_t)p.E * 4u;
-    int w = 0;
-    for (; w + 1 < W; w += 2, base += 2 * stride) variable_words<T, D, 2, POST>(p, ctrl, base, stride, off, llr, v, w);
-    if (w < W) variable_words<T, D, 1, POST>(p, ctrl, base, stride, off, llr, v, w);
+    for (int j = 0; j < D; ++j) off[j] = (uint32_t)p.vedge[j * n + v] * 4u;
+    variable_node<T, D, POST>(p, ctrl, edge, llr, v, W, n, E, off);
 }
 
 // any degree (slow path for degrees without an exact instantiation): two passes over the words
 template <class T>
 __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr,
-                                                  int v, int W, int dv)
+                                                  int v, int W, int dv, int n, int E)
 {
     for (int w = 0; w < W; ++w) {
-        uint32_t *ew = edge + (size_t)w * p.E;
-        typename T::Acc acc = T::acc_init(llr[(size_t)w * p.n + v]);
-        for (int j = 0; j < dv; ++j) T::acc_sub(acc, ew[p.vedge[(size_t)j * p.n + v]]);
+        uint32_t *ew = edge + (size_t)w * E;
+        typename T::Acc acc = T::acc_init(llr[(size_t)w * n + v]);
+        for (int j = 0; j < dv; ++j) T::acc_sub(acc, ew[p.vedge[(size_t)j * n + v]]);
         uint32_t hd, guard = 0;
         const uint32_t pw = T::template post_word<64>(acc, hd);
         for (int j = 0; j < dv; ++j) {
-            uint32_t *q = &ew[p.vedge[(size_t)j * p.n + v]];
+            uint32_t *q = &ew[p.vedge[(size_t)j * n + v]];
             const uint32_t a = T::v2c_signmag(pw, *q);
             guard |= a;
             *q = a | hd;
@@ -536,32 +546,51 @@ __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, 
         if (p.post) {
             for (int lane = 0; lane < T::LANES; ++lane) {
                 const int f = ctrl->fid[w * T::LANES + lane];
-                if (f >= 0) p.post[(size_t)f * p.n + v] = T::lane_value(pw, lane);
+                if (f >= 0) p.post[(size_t)f * n + v] = T::lane_value(pw, lane);
             }
         }
     }
 }
 
-template <class T, int DV, bool POST>
-__device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr, int W)
+// REGV: every variable has degree DV -- the edge addresses of the thread's next variable are fetched while the
+// current one is processed (the table lives in global memory / L2)
+template <class T, int DV, bool POST, bool REGV>
+__device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr, int W,
+                                               int n, int E)
 {
-    for (int v = threadIdx.x; v < p.n; v += blockDim.x) {
+    if (REGV) {
+        int v = threadIdx.x;
+        uint32_t next[DV];
+#pragma unroll
+        for (int j = 0; j < DV; ++j) next[j] = v < n ? (uint32_t)p.vedge[j * n + v] * 4u : 0u;
+        for (; v < n; v += blockDim.x) {
+            uint32_t off[DV];
+#pragma unroll
+            for (int j = 0; j < DV; ++j) off[j] = next[j];
+            const int vn = v + blockDim.x;
+#pragma unroll
+            for (int j = 0; j < DV; ++j) next[j] = vn < n ? (uint32_t)p.vedge[j * n + vn] * 4u : 0u;
+            variable_node<T, DV, POST>(p, ctrl, edge, llr, v, W, n, E, off);
+        }
+        return;
+    }
+    for (int v = threadIdx.x; v < n; v += blockDim.x) {
         const int dv = p.vdeg[v];
         bool done = false;
         if (DV <= 12) {
             // exact-degree bodies: no per-edge predicates or branches inside
             switch (dv) {
-#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), POST>(p, ctrl, edge, llr, v, W); done = true; } break;
+#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), POST>(p, ctrl, edge, llr, v, W, n, E); done = true; } break;
                 LDPC_VCASE(1) LDPC_VCASE(2) LDPC_VCASE(3) LDPC_VCASE(4) LDPC_VCASE(5) LDPC_VCASE(6)
                 LDPC_VCASE(7) LDPC_VCASE(8) LDPC_VCASE(9) LDPC_VCASE(10) LDPC_VCASE(11) LDPC_VCASE(12)
 #undef LDPC_VCASE
             default: break;
             }
         } else if (dv == DV) {
-            variable_node<T, DV, POST>(p, ctrl, edge, llr, v, W);
+            variable_node<T, DV, POST>(p, ctrl, edge, llr, v, W, n, E);
             done = true;
         }
-        if (!done) variable_node_any<T>(p, ctrl, edge, llr, v, W, dv);
+        if (!done) variable_node_any<T>(p, ctrl, edge, llr, v, W, dv, n, E);
     }
 }
 
@@ -570,15 +599,18 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
 //   DC   largest check degree, REG: every check has degree DC
 //   DV   largest variable degree with an exact body
 //   NI   word sets per thread in the check / syndrome phases (W is a multiple of NI)
+//   M, N compile-time m and n of the named codes (0 = read them from the parameters)
 //   MAXT, NCTA  launch bounds: CTA size and co-resident CTAs per SM.  Two CTAs drift out of phase, so
 //        one's latency-bound variable phase overlaps the other's ALU-bound check phase.
 // ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA>
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N>
 __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
-    const int n = p.n, m = p.m, E = p.E, W = p.W;
+    // the named codes get their dimensions as compile-time constants: every k*m word offset of the check
+    // phase then folds into the load/store immediate
+    const int n = N ? N : p.n, m = M ? M : p.m, E = M ? DC * M : p.E, W = p.W;
     uint32_t *edge = smem;                 // [W][E]
     uint32_t *llr = edge + (size_t)W * E;  // [W][n]
     uint32_t *cxor = llr + (size_t)W * n;  // [W][m] inverted XOR of every check's incoming words
@@ -593,6 +625,13 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
     __syncthreads();
     unsigned int trip = 0;
 
+    // Co-resident CTAs run identical trips; started together they would stay in lockstep and both hit the
+    // ALU-bound check phase at the same time.  Offsetting one of them lets its latency-bound phases (variable,
+    // syndrome, bookkeeping) overlap the other's check phase.
+    if (NCTA > 1 && p.stagger > 0 && (int)blockIdx.x >= p.stagger_from) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.stagger) { }
+    }
     uint32_t fin = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);  // slots to (re)fill
     bool first = true;
     const int items = (W / NI) * m;  // (word-set group, check)
@@ -767,8 +806,8 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
         LDPC_MARK(1);
 
         // ---------------------------------------------------------------- variable phase
-        if (p.post) variable_phase<T, DV, true>(p, ctrl, edge, llr, W);
-        else variable_phase<T, DV, false>(p, ctrl, edge, llr, W);
+        if (p.post) variable_phase<T, DV, true, (PREFETCH_VEDGE && M != 0 && REG && DV <= 8)>(p, ctrl, edge, llr, W, n, E);
+        else variable_phase<T, DV, false, (PREFETCH_VEDGE && M != 0 && REG && DV <= 8)>(p, ctrl, edge, llr, W, n, E);
         __syncthreads();
         LDPC_MARK(2);
 
@@ -789,13 +828,26 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
                     check_xors<DC, NI>(e0, m, E, NI, acc);
                 } else {
                     const int d = p.cdeg[c];
+                    bool done = false;
+                    if (DC <= 16) {
+                        switch (d) {
+#define LDPC_XCASE(D) case D: if (D <= DC) { check_xors<(D <= DC ? D : 2), NI>(e0, m, E, NI, acc); done = true; } break;
+                            LDPC_XCASE(2) LDPC_XCASE(3) LDPC_XCASE(4) LDPC_XCASE(5) LDPC_XCASE(6) LDPC_XCASE(7) LDPC_XCASE(8)
+                            LDPC_XCASE(9) LDPC_XCASE(10) LDPC_XCASE(11) LDPC_XCASE(12) LDPC_XCASE(13) LDPC_XCASE(14)
+                            LDPC_XCASE(15) LDPC_XCASE(16)
+#undef LDPC_XCASE
+                        default: break;
+                        }
+                    }
+                    if (!done) {
 #pragma unroll
-                    for (int j = 0; j < NI; ++j) {
-                        uint32_t a = 0;
+                        for (int j = 0; j < NI; ++j) {
+                            uint32_t a = 0;
 #pragma unroll
-                        for (int k = 0; k < DC; ++k)
-                            if (k < d) a ^= e0[(size_t)j * E + k * m];
-                        acc[j] = a;
+                            for (int k = 0; k < DC; ++k)
+                                if (k < d) a ^= e0[(size_t)j * E + k * m];
+                            acc[j] = a;
+                        }
                     }
                 }
 #pragma unroll
