@@ -90,9 +90,13 @@ struct ldpc_decoder {
     uint16_t *d_vedge = nullptr;
     unsigned long long *d_queue = nullptr;  // [2]: packed launch, int32 launch
     Plan plan16, plan32;
-    // host-buffer path staging
-    void *d_llr = nullptr; int *d_iters = nullptr; uint32_t *d_bits = nullptr; int *d_post = nullptr; int *d_v2c = nullptr;
+    // host-buffer path: two staging sets so the H2D copy of chunk i+1, the decode of chunk i and the D2H copy
+    // of chunk i-1 overlap (copy-in / kernel / copy-out streams)
+    void *d_llr[2] = {nullptr, nullptr}; int *d_iters[2] = {nullptr, nullptr}; uint32_t *d_bits[2] = {nullptr, nullptr};
+    int *d_post[2] = {nullptr, nullptr}; int *d_v2c[2] = {nullptr, nullptr};
     size_t cap_frames = 0; bool cap_post = false, cap_v2c = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     // frames flagged by the packed kernel: list, length of the current call, running total
     int *d_fb_index = nullptr, *d_fb_count = nullptr;
     unsigned long long *d_fb_total = nullptr;
@@ -343,23 +347,37 @@ static int mc_scratch(ldpc_decoder &d, size_t frames)
 
 static void free_staging(ldpc_decoder &d)
 {
-    cudaFree(d.d_llr); cudaFree(d.d_iters); cudaFree(d.d_bits); cudaFree(d.d_post); cudaFree(d.d_v2c);
-    d.d_llr = nullptr; d.d_iters = nullptr; d.d_bits = nullptr; d.d_post = nullptr; d.d_v2c = nullptr;
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(d.d_llr[b]); cudaFree(d.d_iters[b]); cudaFree(d.d_bits[b]); cudaFree(d.d_post[b]); cudaFree(d.d_v2c[b]);
+        d.d_llr[b] = nullptr; d.d_iters[b] = nullptr; d.d_bits[b] = nullptr; d.d_post[b] = nullptr; d.d_v2c[b] = nullptr;
+    }
     d.cap_frames = 0; d.cap_post = d.cap_v2c = false;
 }
 
 static int ensure_staging(ldpc_decoder &d, size_t frames, bool post, bool v2c)
 {
+    if (!d.s_in) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&d.s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&d.s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(cudaEventCreateWithFlags(&d.ev_in[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&d.ev_k[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&d.ev_out[b], cudaEventDisableTiming));
+        }
+    }
     if (d.cap_frames >= frames && (!post || d.cap_post) && (!v2c || d.cap_v2c)) return LDPC_OK;
     const ldpc_code &c = d.code;
     size_t cap = std::max(frames, d.cap_frames);
     post |= d.cap_post; v2c |= d.cap_v2c;
+    CUDA_TRY(cudaDeviceSynchronize());
     free_staging(d);
-    CUDA_TRY(cudaMalloc(&d.d_llr, cap * c.n * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d.d_iters, cap * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&d.d_bits, cap * ((c.n + 31) / 32) * sizeof(uint32_t)));
-    if (post) CUDA_TRY(cudaMalloc(&d.d_post, cap * c.n * sizeof(int)));
-    if (v2c) CUDA_TRY(cudaMalloc(&d.d_v2c, cap * (size_t)c.dc_max * c.m * sizeof(int)));
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(cudaMalloc(&d.d_llr[b], cap * c.n * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&d.d_iters[b], cap * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&d.d_bits[b], cap * ((c.n + 31) / 32) * sizeof(uint32_t)));
+        if (post) CUDA_TRY(cudaMalloc(&d.d_post[b], cap * c.n * sizeof(int)));
+        if (v2c) CUDA_TRY(cudaMalloc(&d.d_v2c[b], cap * (size_t)c.dc_max * c.m * sizeof(int)));
+    }
     d.cap_frames = cap; d.cap_post = post; d.cap_v2c = v2c;
     return LDPC_OK;
 }
@@ -558,6 +576,13 @@ void ldpc_decoder_destroy(ldpc_decoder *d)
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
     ldpc::free_staging(*d);
+    for (int b = 0; b < 2; ++b) {
+        if (d->ev_in[b]) cudaEventDestroy(d->ev_in[b]);
+        if (d->ev_k[b]) cudaEventDestroy(d->ev_k[b]);
+        if (d->ev_out[b]) cudaEventDestroy(d->ev_out[b]);
+    }
+    if (d->s_in) cudaStreamDestroy(d->s_in);
+    if (d->s_out) cudaStreamDestroy(d->s_out);
     cudaFree(d->d_cdeg); cudaFree(d->d_vdeg); cudaFree(d->d_vedge); cudaFree(d->d_queue);
     cudaFree(d->d_fb_index); cudaFree(d->d_fb_count); cudaFree(d->d_fb_total);
     cudaFree(d->d_mc_pow); cudaFree(d->d_mc_cw); cudaFree(d->d_mc_info); cudaFree(d->d_mc_pin);
@@ -580,20 +605,39 @@ int ldpc_decode_batch(ldpc_decoder *d, const int32_t *llr, size_t frames, int32_
     if (!d || !llr || !iters) { ldpc::set_error("NULL decoder / llr / iters"); return LDPC_ERR_ARG; }
     if (frames == 0) return LDPC_OK;
     CUDA_TRY(cudaSetDevice(d->device));
-    int rc = ldpc::ensure_staging(*d, frames, post != nullptr, v2c != nullptr);
-    if (rc != LDPC_OK) return rc;
     const ldpc_code &c = d->code;
     const size_t nw32 = (c.n + 31) / 32, vsz = (size_t)c.dc_max * c.m;
-    cudaStream_t st = d->stream;
-    CUDA_TRY(cudaMemcpyAsync(d->d_llr, llr, frames * c.n * sizeof(int), cudaMemcpyHostToDevice, st));
-    rc = ldpc::decode_device(*d, d->d_llr, 32, (long long)frames, d->d_iters, bits ? d->d_bits : nullptr,
-                             post ? d->d_post : nullptr, v2c ? d->d_v2c : nullptr, st);
+    // chunks large enough to fill every frame slot of the device a few times over, small enough that the
+    // copies of one chunk hide behind the decode of its neighbours (pinned host memory makes them asynchronous)
+    const size_t slots = (size_t)d->sm_count * d->plan16.kernel.ctas_per_sm * d->plan16.W * 2;
+    size_t chunk = std::max<size_t>(slots * 4, 8192);
+    if (post || v2c) chunk = std::max<size_t>(slots, 1024);  // parity-mode outputs are large
+    chunk = std::min(chunk, frames);
+    int rc = ldpc::ensure_staging(*d, chunk, post != nullptr, v2c != nullptr);
     if (rc != LDPC_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(iters, d->d_iters, frames * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (bits) CUDA_TRY(cudaMemcpyAsync(bits, d->d_bits, frames * nw32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    if (post) CUDA_TRY(cudaMemcpyAsync(post, d->d_post, frames * c.n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (v2c) CUDA_TRY(cudaMemcpyAsync(v2c, d->d_v2c, frames * vsz * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaStream_t sk = d->stream;
+    size_t index = 0;
+    for (size_t base = 0; base < frames; base += chunk, ++index) {
+        const size_t cnt = std::min(chunk, frames - base);
+        const int b = (int)(index & 1);
+        if (index >= 2) CUDA_TRY(cudaStreamWaitEvent(d->s_in, d->ev_k[b], 0));   // decode of chunk i-2 consumed this buffer
+        CUDA_TRY(cudaMemcpyAsync(d->d_llr[b], llr + base * c.n, cnt * c.n * sizeof(int), cudaMemcpyHostToDevice, d->s_in));
+        CUDA_TRY(cudaEventRecord(d->ev_in[b], d->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(sk, d->ev_in[b], 0));
+        if (index >= 2) CUDA_TRY(cudaStreamWaitEvent(sk, d->ev_out[b], 0));      // results of chunk i-2 have left
+        rc = ldpc::decode_device(*d, d->d_llr[b], 32, (long long)cnt, d->d_iters[b], bits ? d->d_bits[b] : nullptr,
+                                 post ? d->d_post[b] : nullptr, v2c ? d->d_v2c[b] : nullptr, sk);
+        if (rc != LDPC_OK) return rc;
+        CUDA_TRY(cudaEventRecord(d->ev_k[b], sk));
+        CUDA_TRY(cudaStreamWaitEvent(d->s_out, d->ev_k[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(iters + base, d->d_iters[b], cnt * sizeof(int), cudaMemcpyDeviceToHost, d->s_out));
+        if (bits) CUDA_TRY(cudaMemcpyAsync(bits + base * nw32, d->d_bits[b], cnt * nw32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->s_out));
+        if (post) CUDA_TRY(cudaMemcpyAsync(post + base * c.n, d->d_post[b], cnt * c.n * sizeof(int), cudaMemcpyDeviceToHost, d->s_out));
+        if (v2c) CUDA_TRY(cudaMemcpyAsync(v2c + base * vsz, d->d_v2c[b], cnt * vsz * sizeof(int), cudaMemcpyDeviceToHost, d->s_out));
+        CUDA_TRY(cudaEventRecord(d->ev_out[b], d->s_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(d->s_out));
+    CUDA_TRY(cudaStreamSynchronize(sk));
     return LDPC_OK;
 }
 
