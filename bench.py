@@ -313,6 +313,12 @@ def run_gpu_arm(args):
     algo_bytes = 2 * code.n + (code.n + 7) // 8 + 4  # int16 LLR in + packed bits + iteration count out
     per_gpu_fps = fps / world
     achieved = per_gpu_fps * algo_bytes / 1e9
+    traffic = None  # DRAM bytes per launch from the committed ncu capture (profiles/r01/traffic.json)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01", "traffic.json")) as fh:
+            traffic = json.load(fh)[args.code]["dram_bytes_per_frame"] * frames
+    except Exception:
+        pass
     # algorithmic integer work: 18 ops per necessary sxor, 3 per edge, 1 per variable
     _, cdeg, _, _ = code.tables()
     sxors = int((3 * cdeg - 6).sum())
@@ -334,7 +340,8 @@ def run_gpu_arm(args):
         "operating_point": {"ebn0_db": ebn0_op, "avg_iters": it_op, "value": world * frames / (ms_op * 1e-3) * k / 1e9,
                             "unit": "Gbit/s", "frames_per_s": world * frames / (ms_op * 1e-3)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_frame": algo_bytes,
+                     "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes * frames,
+                     "peak_source": peak_src, "algorithmic_bytes_per_frame": algo_bytes,
                      "note": "state is smem-resident; the binding resource is integer issue, see roofline_int"},
         "roofline_int": {"bound": "int32 issue slots (ALU+FMA pipes)", "achieved": int_ach, "peak": int_peak,
                          "unit": "Tops/s", "frac": int_ach / int_peak, "algorithmic_ops_per_frame_iter": ops_iter,
