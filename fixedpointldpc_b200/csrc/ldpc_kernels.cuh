@@ -812,61 +812,81 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
         LDPC_MARK(2);
 
         // ---------------------------------------------------------------- syndrome pass
-        for (int i0 = tid - lane_id; i0 < items; i0 += nthreads) {
-            const int i = i0 + lane_id;
-            const bool valid = i < items;
-            int wg = 0;
-            uint32_t fb[NI];
+        {
+            // When the CTA holds a single word-set group (W == NI) every item votes for the same NI word sets: the
+            // thread ORs its items' verdicts in registers and the warp reduces once, after the loop.
+            const bool one_group = (W == NI);
+            uint32_t mine[NI];
 #pragma unroll
-            for (int j = 0; j < NI; ++j) fb[j] = 0u;
-            if (valid) {
-                wg = (int)__umulhi((uint32_t)i, p.inv_m);
-                const int c = i - wg * m;
-                const uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
-                uint32_t acc[NI];
-                if (REG) {
-                    check_xors<DC, NI>(e0, m, E, NI, acc);
-                } else {
-                    const int d = p.cdeg[c];
-                    bool done = false;
-                    if (DC <= 16) {
-                        switch (d) {
+            for (int j = 0; j < NI; ++j) mine[j] = 0u;
+            for (int i0 = tid - lane_id; i0 < items; i0 += nthreads) {
+                const int i = i0 + lane_id;
+                const bool valid = i < items;
+                int wg = 0;
+                uint32_t fb[NI];
+#pragma unroll
+                for (int j = 0; j < NI; ++j) fb[j] = 0u;
+                if (valid) {
+                    wg = (int)__umulhi((uint32_t)i, p.inv_m);
+                    const int c = i - wg * m;
+                    const uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
+                    uint32_t acc[NI];
+                    if (REG) {
+                        check_xors<DC, NI>(e0, m, E, NI, acc);
+                    } else {
+                        const int d = p.cdeg[c];
+                        bool done = false;
+                        if (DC <= 16) {
+                            switch (d) {
 #define LDPC_XCASE(D) case D: if (D <= DC) { check_xors<(D <= DC ? D : 2), NI>(e0, m, E, NI, acc); done = true; } break;
-                            LDPC_XCASE(2) LDPC_XCASE(3) LDPC_XCASE(4) LDPC_XCASE(5) LDPC_XCASE(6) LDPC_XCASE(7) LDPC_XCASE(8)
-                            LDPC_XCASE(9) LDPC_XCASE(10) LDPC_XCASE(11) LDPC_XCASE(12) LDPC_XCASE(13) LDPC_XCASE(14)
-                            LDPC_XCASE(15) LDPC_XCASE(16)
+                                LDPC_XCASE(2) LDPC_XCASE(3) LDPC_XCASE(4) LDPC_XCASE(5) LDPC_XCASE(6) LDPC_XCASE(7) LDPC_XCASE(8)
+                                LDPC_XCASE(9) LDPC_XCASE(10) LDPC_XCASE(11) LDPC_XCASE(12) LDPC_XCASE(13) LDPC_XCASE(14)
+                                LDPC_XCASE(15) LDPC_XCASE(16)
 #undef LDPC_XCASE
-                        default: break;
+                            default: break;
+                            }
+                        }
+                        if (!done) {
+#pragma unroll
+                            for (int j = 0; j < NI; ++j) {
+                                uint32_t a = 0;
+#pragma unroll
+                                for (int k = 0; k < DC; ++k)
+                                    if (k < d) a ^= e0[(size_t)j * E + k * m];
+                                acc[j] = a;
+                            }
                         }
                     }
-                    if (!done) {
 #pragma unroll
-                        for (int j = 0; j < NI; ++j) {
-                            uint32_t a = 0;
-#pragma unroll
-                            for (int k = 0; k < DC; ++k)
-                                if (k < d) a ^= e0[(size_t)j * E + k * m];
-                            acc[j] = a;
-                        }
+                    for (int j = 0; j < NI; ++j) {
+                        cxor[(size_t)(wg * NI + j) * m + c] = ~acc[j];
+                        fb[j] = T::fail_bits(acc[j]);
                     }
                 }
+                if (one_group) {
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) mine[j] |= fb[j];
+                    continue;
+                }
+                const int g0 = __shfl_sync(0xffffffffu, wg, 0);
+                // a warp covers at most two word-set groups when m >= 32; anything else goes the slow way
 #pragma unroll
                 for (int j = 0; j < NI; ++j) {
-                    cxor[(size_t)(wg * NI + j) * m + c] = ~acc[j];
-                    fb[j] = T::fail_bits(acc[j]);
+                    const uint32_t r0 = __reduce_or_sync(0xffffffffu, (valid && wg == g0) ? fb[j] : 0u);
+                    const uint32_t r1 = __reduce_or_sync(0xffffffffu, (valid && wg == g0 + 1) ? fb[j] : 0u);
+                    if (lane_id == 0) {
+                        if (r0) atomicOr(&ctrl->fail[g0 * NI + j], r0);
+                        if (r1) atomicOr(&ctrl->fail[(g0 + 1) * NI + j], r1);
+                    }
+                    if (valid && wg > g0 + 1 && fb[j]) atomicOr(&ctrl->fail[wg * NI + j], fb[j]);
                 }
             }
-            const int g0 = __shfl_sync(0xffffffffu, wg, 0);
-            // a warp covers at most two word-set groups when m >= 32; anything else goes the slow way
+            if (one_group && tid - lane_id < items) {
 #pragma unroll
-            for (int j = 0; j < NI; ++j) {
-                const uint32_t r0 = __reduce_or_sync(0xffffffffu, (valid && wg == g0) ? fb[j] : 0u);
-                const uint32_t r1 = __reduce_or_sync(0xffffffffu, (valid && wg == g0 + 1) ? fb[j] : 0u);
-                if (lane_id == 0) {
-                    if (r0) atomicOr(&ctrl->fail[g0 * NI + j], r0);
-                    if (r1) atomicOr(&ctrl->fail[(g0 + 1) * NI + j], r1);
+                for (int j = 0; j < NI; ++j) {
+                    const uint32_t r = __reduce_or_sync(0xffffffffu, mine[j]);
+                    if (lane_id == 0 && r) atomicOr(&ctrl->fail[j], r);
                 }
-                if (valid && wg > g0 + 1 && fb[j]) atomicOr(&ctrl->fail[wg * NI + j], fb[j]);
             }
         }
         __syncthreads();
