@@ -18,7 +18,8 @@
  * Differences from the reference that a caller can observe (each one fenced on purpose):
  *   - decode_fixpoint without a preceding setState(PCV) while the FSM sits in C2V (the reference would keep
  *     iterating on the previous frame's messages, quirk Q7) is rejected: it prints to cerr and returns -1;
- *   - after a pre-check hit (return 0) getPost_fp() returns the channel values, not stale ones (quirk Q6);
+ *   - (kept, not fenced) after a pre-check hit decode_fixpoint returns 0 and Posteriori_fp / EdgeRAM keep the
+ *     previous frame's values exactly like the reference (quirk Q6); only the batch C ABI reports channel values;
  *   - check_fp(int*) evaluates the intended parity check (the reference indexes out of range, :224);
  *   - decode_general(const double*) (dead double-precision path) is not provided by the engine: returns -1;
  *   - I/O errors throw std::runtime_error instead of system("pause"); exit(0).
@@ -79,6 +80,21 @@ public:
 private:
     int CirShift[NUM_CGRP][NUM_VGRP];
     double CodeRate;
+};
+
+/* One edge-slot bank of the message memory (reference :85-106): bank = slot of the edge inside its check,
+ * address = check index.  The engine keeps the messages in GPU shared memory in exactly this [slot][check]
+ * order; this class is the host-side view of the image the last decode left (FP_Decoder::getEdgeRAM). */
+class Memory {
+public:
+    Memory() : Address(0), BRAM_fp(RAM_DEPTH, 0) {}
+    int rdData() { return BRAM_fp[Address]; }
+    void wrtData(int in) { BRAM_fp[Address] = in; }
+    void setAddress(int Addr) { Address = Addr; }
+
+private:
+    int Address;
+    std::vector<int> BRAM_fp;
 };
 
 class ControlFSM {
@@ -201,6 +217,13 @@ public:
     /* --- extensions used by the facade drivers and the tests --- */
     int getDecodedBit(int Addr) { return DecodedCodeword[Addr]; }
     int getEdge(int slot, int chk) { return EdgeRAM_fp[(size_t)slot * m_ + chk]; } /* EdgeRAM[slot].BRAM_fp[chk] */
+    Memory getEdgeRAM(int slot)                                                    /* copy of bank `slot` */
+    {
+        Memory bank;
+        for (int c = 0; c < m_ && c < RAM_DEPTH; c++) { bank.setAddress(c); bank.wrtData(getEdge(slot, c)); }
+        bank.setAddress(0);
+        return bank;
+    }
     int getInfoIndexAt(int i) { return InfoIndex[i]; }
     int getTrueInfoBit(int i) { return TrueInfoBit[i]; }
     ldpc_decoder *engine(bool fixpoint) { ensure_decoder(); return fixpoint ? dec_pre : dec_gen; }

@@ -214,3 +214,34 @@ def test_random_message_simulation_with_per_frame_codewords(fp, golden):
     # hard decisions of the noiseless part agree with the codeword sign convention (bit 1 -> negative LLR)
     assert ((llr < 0) == (sent == 1)).mean() > 0.9
     dec.close()
+
+
+def test_array_debug_flow_20000_frames_known_answer(fp, golden):
+    """ArrayLDPC_Debug flow (A5, 4.5 dB, decode_fixpoint, reference noise from the default seed):
+    the first 20 000 frames hold 993 frame errors, 27 011 info-bit errors and the recorded iteration histogram."""
+    code = fp.codes.array_p47_r5()
+    dec = fp.Decoder(code, precheck=True)
+    snr = 2 * 10 ** (4.5 / 10) * code.rate
+    out = dec.mc_run(20000, snr, stream=fp.STREAM_REFERENCE, seed=123456789, codeword=golden["a5_codeword"],
+                     info_index=golden["a5_info_index"], want_iters=True)
+    assert out["frame_errors"] == 993 and out["bit_errors"] == 27011
+    hist = np.bincount(out["iters"], minlength=31)
+    assert [hist[1], hist[2], hist[3], hist[4], hist[5], hist[30]] == [8, 920, 4697, 5037, 3115, 1022]
+    dec.close()
+
+
+def test_philox_fer_agrees_with_reference_stream_within_confidence(fp, golden):
+    """Different noise stream, same statistics: the frame error rate at 2 dB (802.11) measured with the Philox
+    stream must be compatible with the reference's 100 / 393 214 (two-sample z-test, |z| < 3)."""
+    code = fp.codes.wifi_1944_r12()
+    dec = fp.Decoder(code)
+    frames = 400000
+    out = dec.mc_run(frames, WIFI_SNR_2DB, stream=fp.STREAM_PHILOX, seed=2026, codeword=golden["wifi_codeword"],
+                     info_index=golden["wifi_info_index"], want_frame_err=False)
+    p1, n1, p2, n2 = out["frame_errors"] / frames, frames, 100 / 393214, 393214
+    pooled = (out["frame_errors"] + 100) / (n1 + n2)
+    z = (p1 - p2) / np.sqrt(pooled * (1 - pooled) * (1 / n1 + 1 / n2))
+    assert abs(z) < 3, (out["frame_errors"], z)
+    # bit errors per failed frame are of the reference's order (2732 / 100)
+    assert 10 < out["bit_errors"] / max(1, out["frame_errors"]) < 60
+    dec.close()
