@@ -55,16 +55,19 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
     for (int d : c.vdeg) vregular &= (d == c.dv_max);
     // the four named codes: dimensions are compile-time constants (the REGV variable phase also assumes a
     // uniform variable degree, which all three array codes have)
+    // Launch shapes below were chosen by measurement on B200 (profiles/r01/launch_shape_sweep.txt): for the long
+    // checks more, smaller CTAs with one chain per thread beat two interleaved chains per thread (fewer registers,
+    // half the unrolled code, four independent phase streams per SM); the short 802.11 checks prefer NI = 2.
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 5 && c.m == 235 && c.n == 2209)
-        return make_choice<T, 47, true, 5, 2, 256, 2, 235, 2209>();     // array p47 r5
+        return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209>();     // array p47 r5
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 24 && c.m == 1128 && c.n == 2209)
         return make_choice<T, 47, true, 24, 1, 768, 1, 1128, 2209>();   // array p47 r24
     if (regular && vregular && c.dc_max == 28 && c.dv_max == 4 && c.m == 316 && c.n == 2212)
-        return make_choice<T, 28, true, 4, 2, 384, 2, 316, 2212>();     // cut79
+        return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212>();     // cut79
     if (c.dc_max == 8 && c.dv_max <= 12 && c.m == 972 && c.n == 1944)
         return make_choice<T, 8, false, 12, 2, 512, 2, 972, 1944>();    // 802.11n 1944 r1/2
     // any other code: run-time dimensions
-    if (regular && c.dc_max == 47 && c.dv_max <= 5) return make_choice<T, 47, true, 5, 2, 256, 2, 0, 0>();
+    if (regular && c.dc_max == 47 && c.dv_max <= 5) return make_choice<T, 47, true, 5, 1, 256, 4, 0, 0>();
     if (c.dc_max <= 8 && c.dv_max <= 12) return make_choice<T, 8, false, 12, 2, 512, 2, 0, 0>();
     if (c.dc_max <= 64 && c.dv_max <= 32) return make_choice<T, 64, false, 32, 1, 512, 1, 0, 0>();
     return KernelChoice();
@@ -83,7 +86,6 @@ struct ldpc_decoder {
     ldpc_code code;
     ldpc_decoder_cfg cfg;
     int device = 0, sm_count = 0, max_smem = 0;
-    int stagger_cycles = 0;
     cudaStream_t stream = nullptr;
     // device tables
     uint8_t *d_cdeg = nullptr, *d_vdeg = nullptr;
@@ -202,8 +204,6 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     p.n = c.n; p.m = c.m; p.E = c.dc_max * c.m; p.dc_max = c.dc_max; p.dv_max = c.dv_max;
     p.W = pl.W; p.max_iter = d.cfg.max_iter; p.precheck = d.cfg.precheck;
     p.inv_m = (uint32_t)((1ull << 32) / (unsigned)c.m) + 1u;
-    p.stagger = pl.kernel.ctas_per_sm > 1 ? d.stagger_cycles : 0;
-    p.stagger_from = d.sm_count;
     p.llr = llr; p.llr_bits = llr_bits; p.frames = frames;
     p.iters = iters; p.bits = bits; p.nw32 = (c.n + 31) / 32; p.post = post; p.v2c = v2c;
     p.queue = d.d_queue + which;
@@ -559,7 +559,6 @@ ldpc_decoder *ldpc_decoder_create(const ldpc_code *code, const ldpc_decoder_cfg 
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&d->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg.device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { ldpc::set_error(cudaGetErrorString(e)); return fail(LDPC_ERR_CUDA); }
-    if (const char *env = getenv("LDPC_STAGGER_CYCLES")) d->stagger_cycles = atoi(env);
     if ((st = ldpc::upload_tables(*d)) != LDPC_OK) return fail(st);
     if ((st = ldpc::make_plan(*d, 2, ldpc::pick_kernel<ldpc::Packed16>(d->code), cfg.threads, cfg.frames_per_cta, d->plan16)) != LDPC_OK) return fail(st);
     if ((st = ldpc::make_plan(*d, 1, ldpc::pick_kernel<ldpc::Scalar32>(d->code), cfg.threads, cfg.frames_per_cta, d->plan32)) != LDPC_OK) return fail(st);

@@ -42,8 +42,6 @@ struct KParams {
     int W;         // word sets per CTA
     int max_iter;  // MAX_ITER; 0 = hard decision + syndrome only (iters output: 0 pass, 1 fail)
     uint32_t inv_m;  // floor(2^32 / m) + 1: i / m == umulhi(i, inv_m) for i < 2^16
-    int stagger;     // cycles the second CTA of every SM waits before its first trip (phase offset)
-    int stagger_from;  // first blockIdx.x that waits
     int precheck;  // decode_fixpoint's hardDecision pre-check
     // io
     const void *llr;  // [frames][n] int32 or int16
@@ -625,13 +623,6 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
     __syncthreads();
     unsigned int trip = 0;
 
-    // Co-resident CTAs run identical trips; started together they would stay in lockstep and both hit the
-    // ALU-bound check phase at the same time.  Offsetting one of them lets its latency-bound phases (variable,
-    // syndrome, bookkeeping) overlap the other's check phase.
-    if (NCTA > 1 && p.stagger > 0 && (int)blockIdx.x >= p.stagger_from) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < p.stagger) { }
-    }
     uint32_t fin = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);  // slots to (re)fill
     bool first = true;
     const int items = (W / NI) * m;  // (word-set group, check)
