@@ -32,6 +32,7 @@ struct KernelChoice {
     int max_threads = 0;
     int ni = 1;
     int ctas_per_sm = 1;
+    bool cdeg_in_smem = false, vdeg_in_smem = false;
 };
 
 template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N> static KernelChoice make_choice()
@@ -41,6 +42,9 @@ template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, 
     k.max_threads = MAXT;
     k.ni = NI;
     k.ctas_per_sm = NCTA;
+    // shared-memory copies of the degree tables (must mirror the kernel's REG / REGV conditions)
+    k.cdeg_in_smem = !REG;
+    k.vdeg_in_smem = !(PREFETCH_VEDGE && M != 0 && REG && DV <= 8);
     return k;
 }
 
@@ -124,7 +128,8 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
     const int per_w = (c.dc_max * c.m + c.n + c.m) * 4;  // messages + channel values + per-check XOR
     // co-resident CTAs share the SM's shared memory (228 KB minus 1 KB reserved per CTA)
     const int sm_total = d.max_smem + 1024;
-    const int budget = (k.ctas_per_sm > 1 ? sm_total / k.ctas_per_sm - 1024 : d.max_smem) - (int)sizeof(Ctrl) - 64;
+    const int tables = (k.cdeg_in_smem ? ((c.m + 15) & ~15) : 0) + (k.vdeg_in_smem ? ((c.n + 15) & ~15) : 0);
+    const int budget = (k.ctas_per_sm > 1 ? sm_total / k.ctas_per_sm - 1024 : d.max_smem) - (int)sizeof(Ctrl) - tables - 64;
     int W = std::min(budget / per_w, (int)MAX_W);
     if (want_slots > 0) {  // override, rounded up to whole groups of NI word sets
         int w = std::max(1, (want_slots + lanes - 1) / lanes);
@@ -151,7 +156,7 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
     }
     if (want_threads > 0) best_t = std::min(k.max_threads, std::max(32, (want_threads / 32) * 32));
     out.kernel = k; out.W = W; out.threads = best_t;
-    out.smem = W * per_w + (int)sizeof(Ctrl);
+    out.smem = W * per_w + (int)sizeof(Ctrl) + tables;
     cudaError_t e = cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, out.smem);
     if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return LDPC_ERR_CUDA; }
     return LDPC_OK;

@@ -554,7 +554,7 @@ __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, 
 // current one is processed (the table lives in global memory / L2)
 template <class T, int DV, bool POST, bool REGV>
 __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr, int W,
-                                               int n, int E)
+                                               int n, int E, const uint8_t *vdeg)
 {
     if (REGV) {
         int v = threadIdx.x;
@@ -573,7 +573,7 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
         return;
     }
     for (int v = threadIdx.x; v < n; v += blockDim.x) {
-        const int dv = p.vdeg[v];
+        const int dv = vdeg[v];
         bool done = false;
         if (DV <= 12) {
             // exact-degree bodies: no per-edge predicates or branches inside
@@ -613,6 +613,12 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
     uint32_t *llr = edge + (size_t)W * E;  // [W][n]
     uint32_t *cxor = llr + (size_t)W * n;  // [W][m] inverted XOR of every check's incoming words
     Ctrl *ctrl = reinterpret_cast<Ctrl *>(cxor + (size_t)W * m);
+    // degree tables next to the control block (irregular codes dispatch on them once per node and phase)
+    constexpr bool REGV = PREFETCH_VEDGE && M != 0 && REG && DV <= 8;
+    uint8_t *cdeg_s = reinterpret_cast<uint8_t *>(ctrl + 1);
+    uint8_t *vdeg_s = cdeg_s + (REG ? 0 : ((m + 15) & ~15));
+    if (!REG) for (int i = tid; i < m; i += nthreads) cdeg_s[i] = p.cdeg[i];
+    if (!REGV) for (int i = tid; i < n; i += nthreads) vdeg_s[i] = p.vdeg[i];
     const int nslots = W * T::LANES;
     const long long frames = p.count ? (long long)*p.count : p.frames;
 
@@ -653,7 +659,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
                             const int v = v0 + tid;
                             uint32_t b = 0;
                             if (v < n) {
-                                if (p.vdeg[v]) b = T::hd_bit(ew[p.vedge[v]], lane);
+                                if (REGV || vdeg_s[v]) b = T::hd_bit(ew[p.vedge[v]], lane);
                                 else b = T::lane_value(llr[(size_t)w * n + v], lane) <= 0;
                             }
                             const uint32_t word = __ballot_sync(0xffffffffu, b);
@@ -685,7 +691,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
                         int *out = p.v2c + (size_t)f * p.dc_max * m;
                         for (int i = tid; i < p.dc_max * m; i += nthreads) {
                             const int k = i / m, c = i - k * m;
-                            out[i] = k < (REG ? DC : (int)p.cdeg[c]) ? T::v2c_value(ew[i], lane) : 0;
+                            out[i] = k < (REG ? DC : (int)cdeg_s[c]) ? T::v2c_value(ew[i], lane) : 0;
                         }
                     }
                 }
@@ -777,7 +783,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
             if (REG) {
                 check_nodes<T, DC, NI>(e0, m, E, nacc0, NI);
             } else {
-                const int d = p.cdeg[c];
+                const int d = cdeg_s[c];
                 bool done = false;
                 if (DC <= 16) {
                     switch (d) {
@@ -797,8 +803,8 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
         LDPC_MARK(1);
 
         // ---------------------------------------------------------------- variable phase
-        if (p.post) variable_phase<T, DV, true, (PREFETCH_VEDGE && M != 0 && REG && DV <= 8)>(p, ctrl, edge, llr, W, n, E);
-        else variable_phase<T, DV, false, (PREFETCH_VEDGE && M != 0 && REG && DV <= 8)>(p, ctrl, edge, llr, W, n, E);
+        if (p.post) variable_phase<T, DV, true, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
+        else variable_phase<T, DV, false, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
         __syncthreads();
         LDPC_MARK(2);
 
@@ -825,7 +831,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
                     if (REG) {
                         check_xors<DC, NI>(e0, m, E, NI, acc);
                     } else {
-                        const int d = p.cdeg[c];
+                        const int d = cdeg_s[c];
                         bool done = false;
                         if (DC <= 16) {
                             switch (d) {
