@@ -33,12 +33,14 @@ struct KernelChoice {
     int ni = 1;
     int ctas_per_sm = 1;
     bool cdeg_in_smem = false, vdeg_in_smem = false;
+    int ipt = 0;  // > 0: fused schedule, at most ipt check items per thread
 };
 
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N> static KernelChoice make_choice()
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int IPT> static KernelChoice make_choice()
 {
     KernelChoice k;
-    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N>;
+    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, IPT>;
+    k.ipt = IPT;
     k.max_threads = MAXT;
     k.ni = NI;
     k.ctas_per_sm = NCTA;
@@ -62,18 +64,20 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
     // Launch shapes below were chosen by measurement on B200 (profiles/r01/launch_shape_sweep.txt): for the long
     // checks more, smaller CTAs with one chain per thread beat two interleaved chains per thread (fewer registers,
     // half the unrolled code, four independent phase streams per SM); the short 802.11 checks prefer NI = 2.
-    if (regular && vregular && c.dc_max == 47 && c.dv_max == 5 && c.m == 235 && c.n == 2209)
-        return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209>();     // array p47 r5
+    // fused schedule (IPT > 0) where every check item fits one thread without spilling: +4 % on the long-check
+    // array codes; the 802.11 code (two items x two word sets per thread at 64 registers) is faster unfused
+    if (regular && vregular && c.dc_max == 47 && c.dv_max == 5 && c.m == 235 && c.n == 2209)          // array p47 r5
+        return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209, 1>();
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 24 && c.m == 1128 && c.n == 2209)
-        return make_choice<T, 47, true, 24, 1, 768, 1, 1128, 2209>();   // array p47 r24
-    if (regular && vregular && c.dc_max == 28 && c.dv_max == 4 && c.m == 316 && c.n == 2212)
-        return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212>();     // cut79
-    if (c.dc_max == 8 && c.dv_max <= 12 && c.m == 972 && c.n == 1944)
-        return make_choice<T, 8, false, 12, 2, 512, 2, 972, 1944>();    // 802.11n 1944 r1/2
+        return make_choice<T, 47, true, 24, 1, 768, 1, 1128, 2209, 0>();   // array p47 r24
+    if (regular && vregular && c.dc_max == 28 && c.dv_max == 4 && c.m == 316 && c.n == 2212)          // cut79
+        return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212, 1>();
+    if (c.dc_max == 8 && c.dv_max <= 12 && c.m == 972 && c.n == 1944)                                // 802.11n 1944 r1/2
+        return make_choice<T, 8, false, 12, 2, 512, 2, 972, 1944, 0>();
     // any other code: run-time dimensions
-    if (regular && c.dc_max == 47 && c.dv_max <= 5) return make_choice<T, 47, true, 5, 1, 256, 4, 0, 0>();
-    if (c.dc_max <= 8 && c.dv_max <= 12) return make_choice<T, 8, false, 12, 2, 512, 2, 0, 0>();
-    if (c.dc_max <= 64 && c.dv_max <= 32) return make_choice<T, 64, false, 32, 1, 512, 1, 0, 0>();
+    if (regular && c.dc_max == 47 && c.dv_max <= 5) return make_choice<T, 47, true, 5, 1, 256, 4, 0, 0, 0>();
+    if (c.dc_max <= 8 && c.dv_max <= 12) return make_choice<T, 8, false, 12, 2, 512, 2, 0, 0, 0>();
+    if (c.dc_max <= 64 && c.dv_max <= 32) return make_choice<T, 64, false, 32, 1, 512, 1, 0, 0, 0>();
     return KernelChoice();
 }
 
@@ -155,6 +159,11 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
         if (e >= best_e - 0.03) best_t = t;  // largest CTA within 3% of the best lane efficiency
     }
     if (want_threads > 0) best_t = std::min(k.max_threads, std::max(32, (want_threads / 32) * 32));
+    if (k.ipt > 0) {  // fused schedule: every check item must have a thread that keeps its forward results
+        const int need = (((items + k.ipt - 1) / k.ipt) + 31) / 32 * 32;
+        if (need > k.max_threads) { set_error("fused schedule: too many check items per CTA"); return LDPC_ERR_UNSUPPORTED; }
+        best_t = std::max(best_t, need);
+    }
     out.kernel = k; out.W = W; out.threads = best_t;
     out.smem = W * per_w + (int)sizeof(Ctrl) + tables;
     cudaError_t e = cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, out.smem);

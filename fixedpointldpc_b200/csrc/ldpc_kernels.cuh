@@ -593,15 +593,254 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
 }
 
 // ------------------------------------------------------------------------------------------
+// split check node for the fused schedule: the forward pass also yields the XOR of the incoming
+// words (syndrome + sign parity), the backward pass runs after the stop decision
+// ------------------------------------------------------------------------------------------
+template <int DC, int NI> struct CheckState {
+    uint32_t fwd[NI][DC - 1];
+    uint32_t w0[NI];
+    uint32_t acc[NI];
+};
+
+template <class T, int D, int DC, int NI>
+__device__ __forceinline__ void check_forward(const uint32_t *e0, int m, int wstride, CheckState<DC, NI> &st)
+{
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        st.w0[i] = e0[i * wstride];
+        st.acc[i] = st.w0[i];
+        st.fwd[i][0] = st.w0[i] & T::MAG;
+    }
+#pragma unroll
+    for (int k = 1; k < D; ++k)
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const uint32_t w = e0[i * wstride + k * m];
+            st.acc[i] ^= w;
+            if (k < D - 1) st.fwd[i][k] = T::g(st.fwd[i][k - 1], w & T::MAG);
+        }
+}
+
+template <class T, int D, int DC, int NI>
+__device__ __forceinline__ void check_backward(uint32_t *e0, int m, int wstride, const CheckState<DC, NI> &st)
+{
+    uint32_t bwd[NI];
+#pragma unroll
+    for (int k = D - 1; k >= 1; --k)
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            uint32_t *e = e0 + i * wstride;
+            const uint32_t w = e[k * m];
+            const uint32_t mag = w & T::MAG;
+            uint32_t o;
+            if (k == D - 1) {
+                o = st.fwd[i][D - 2];
+                bwd[i] = mag;
+            } else {
+                o = T::g(st.fwd[i][k - 1], bwd[i]);
+                bwd[i] = T::g(bwd[i], mag);
+            }
+            e[k * m] = T::neg_c2v(o, ~st.acc[i] ^ w);
+        }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) e0[i * wstride] = T::neg_c2v(bwd[i], ~st.acc[i] ^ st.w0[i]);
+}
+
+#define LDPC_DEGREE_SWITCH(d, DCMAX, CALL)                                                             \
+    switch (d) {                                                                                       \
+        case 2: { constexpr int D = 2 <= DCMAX ? 2 : 2; CALL; } break;                                   \
+        case 3: { constexpr int D = 3 <= DCMAX ? 3 : 2; CALL; } break;                                   \
+        case 4: { constexpr int D = 4 <= DCMAX ? 4 : 2; CALL; } break;                                   \
+        case 5: { constexpr int D = 5 <= DCMAX ? 5 : 2; CALL; } break;                                   \
+        case 6: { constexpr int D = 6 <= DCMAX ? 6 : 2; CALL; } break;                                   \
+        case 7: { constexpr int D = 7 <= DCMAX ? 7 : 2; CALL; } break;                                   \
+        case 8: { constexpr int D = 8 <= DCMAX ? 8 : 2; CALL; } break;                                   \
+        default: break;                                                                                \
+    }
+
+// ------------------------------------------------------------------------------------------
+// results of the slots in `fin` (unless `first`), then refill them from the frame queue.
+// Returns the number of active slots.  Called by every thread of the CTA (contains barriers).
+// ------------------------------------------------------------------------------------------
+template <class T, int DC, bool REG, bool REGV>
+__device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
+                                                 const uint8_t *cdeg_s, const uint8_t *vdeg_s, uint32_t fin, bool first,
+                                                 int n, int m, int E, int W, long long frames)
+{
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
+    const int nslots = W * T::LANES;
+    if (!first) {
+        // results of the frames that stop now (smem state == after their last variable phase)
+        for (int s = 0; s < nslots; ++s) {
+            if (!((fin >> s) & 1u)) continue;
+            const int w = s / T::LANES, lane = s % T::LANES;
+            const int f = ctrl->fid[s];
+            const bool overflow = (ctrl->gflag[w] >> lane) & 1u;
+            if (tid == 0)
+                p.iters[f] = overflow ? -1 : (p.max_iter == 0 ? (int)((ctrl->failed[w] >> lane) & 1u) : ctrl->it[s]);
+            const uint32_t *ew = edge + (size_t)w * E;
+            const bool count_errors = p.mc_mode != 0 && !overflow;
+            if (p.bits || count_errors) {
+                unsigned int errs = 0;
+                for (int v0 = 0; v0 < n; v0 += nthreads) {
+                    const int v = v0 + tid;
+                    uint32_t b = 0;
+                    if (v < n) {
+                        if (REGV || vdeg_s[v]) b = T::hd_bit(ew[p.vedge[v]], lane);
+                        else b = T::lane_value(llr[(size_t)w * n + v], lane) <= 0;
+                    }
+                    const uint32_t word = __ballot_sync(0xffffffffu, b);
+                    if (lane_id == 0 && v < n) {
+                        if (p.bits) p.bits[(size_t)f * p.nw32 + (v >> 5)] = word;
+                        if (count_errors) {
+                            const uint32_t sent = p.mc_cw ? p.mc_cw[(size_t)f * p.mc_cw_stride + (v >> 5)] : 0u;
+                            const uint32_t mask = p.mc_info ? p.mc_info[v >> 5] : 0xffffffffu;
+                            errs += __popc((word ^ sent) & mask);
+                        }
+                    }
+                }
+                if (count_errors) {
+                    if (tid == 0) ctrl->errs = 0u;
+                    __syncthreads();
+                    if (errs) atomicAdd(&ctrl->errs, errs);
+                    __syncthreads();
+                    if (tid == 0) {
+                        const unsigned int e = ctrl->errs;
+                        if (p.mc_frame_err) p.mc_frame_err[f] = (unsigned short)min(e, 65535u);
+                        atomicAdd(&p.mc_counters[0], 1ull);
+                        if (e) atomicAdd(&p.mc_counters[1], 1ull);
+                        if (e) atomicAdd(&p.mc_counters[2], (unsigned long long)e);
+                        atomicAdd(&p.mc_counters[3], (unsigned long long)ctrl->it[s]);
+                    }
+                }
+            }
+            if (p.v2c) {
+                int *out = p.v2c + (size_t)f * p.dc_max * m;
+                for (int i = tid; i < p.dc_max * m; i += nthreads) {
+                    const int k = i / m, c = i - k * m;
+                    out[i] = k < (REG ? DC : (int)cdeg_s[c]) ? T::v2c_value(ew[i], lane) : 0;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        for (int s = 0; s < nslots; ++s) {
+            if (!((fin >> s) & 1u)) continue;
+            const int w = s / T::LANES, lane = s % T::LANES;
+            const unsigned long long f = atomicAdd(p.queue, 1ull);
+            ctrl->fid[s] = f < (unsigned long long)frames ? (p.index ? p.index[f] : (int)f) : -1;
+            if (p.mc_mode == 2 && ctrl->fid[s] >= 0)
+                ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed,
+                                             lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)ctrl->fid[s]));
+            ctrl->it[s] = 0;
+            ctrl->fresh[w] |= 1u << lane;
+            ctrl->gflag[w] &= ~(1u << lane);
+        }
+    }
+    __syncthreads();
+    for (int s = 0; s < nslots; ++s) {
+        if (!((fin >> s) & 1u)) continue;
+        const int w = s / T::LANES, lane = s % T::LANES;
+        const int f = ctrl->fid[s];
+        // a new frame starts from all-zero messages: the check phase maps zeros to zeros and the variable
+        // phase then produces post = LLR, v2c = LLR, which is the reference's initialisation (:45-61)
+        if (T::LANES == 1) {
+            if (!first) for (int i = tid; i < E; i += nthreads) edge[(size_t)w * E + i] = 0u;
+        } else {
+            const uint32_t keep = ~T::lane_mask(lane);
+            if (!first) for (int i = tid; i < E; i += nthreads) edge[(size_t)w * E + i] &= keep;
+        }
+        bool any_bad = false;
+        if (p.mc_mode == 1 && f >= 0) {
+            const unsigned long long g = p.mc_first + (unsigned long long)f;
+            for (int q = tid; 4 * q < n; q += nthreads) {
+                float z[4];
+                philox_normals(p, g, (uint32_t)q, z);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const int v = 4 * q + h;
+                    if (v < n) {
+                        bool bad;
+                        uint32_t *dst = &llr[(size_t)w * n + v];
+                        *dst = T::set_lane(*dst, lane, quantise_llr(p, (double)z[h], cw_bit(p, f, v)), bad);
+                        any_bad |= bad;
+                    }
+                }
+            }
+        } else {
+            for (int v = tid; v < n; v += nthreads) {
+                int val = 0;
+                if (f >= 0) {
+                    if (p.mc_mode == 2)
+                        val = quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], p.mc_pow[v])), cw_bit(p, f, v));
+                    else
+                        val = p.llr_bits == 16 ? (int)reinterpret_cast<const int16_t *>(p.llr)[(size_t)f * n + v]
+                                               : reinterpret_cast<const int *>(p.llr)[(size_t)f * n + v];
+                }
+                bool bad;
+                uint32_t *dst = &llr[(size_t)w * n + v];
+                *dst = T::set_lane(*dst, lane, val, bad);
+                any_bad |= bad;
+            }
+        }
+        if (p.mc_mode != 0 && p.mc_pin_count > 0 && f >= 0) {
+            __syncthreads();
+            for (int i = tid; i < p.mc_pin_count; i += nthreads) {
+                bool bad;
+                uint32_t *dst = &llr[(size_t)w * n + p.mc_pin[i]];
+                *dst = T::set_lane(*dst, lane, p.mc_pin_value, bad);
+            }
+        }
+        if (any_bad) atomicOr(&ctrl->gflag[w], 1u << lane);
+    }
+    __syncthreads();
+    int active = 0;
+    for (int s = 0; s < nslots; ++s) active += ctrl->fid[s] >= 0;
+    return active;
+}
+
+// stop / continue decision of every slot after the syndrome is known; returns the mask of stopping slots
+template <class T>
+__device__ __forceinline__ uint32_t bookkeeping(const KParams &p, Ctrl *ctrl, int W, unsigned int &trip)
+{
+    const int tid = threadIdx.x, nslots = W * T::LANES;
+    // one thread per slot decides; the stop mask travels through shared memory (double buffered by trip
+    // parity so it can be cleared without another barrier)
+    if (tid < nslots) {
+        const int s = tid, w = s / T::LANES, lane = s % T::LANES;
+        if (ctrl->fid[s] >= 0) {
+            const bool fresh = (ctrl->fresh[w] >> lane) & 1u;
+            const int it = ctrl->it[s] + (fresh ? 0 : 1);
+            const bool pass = !((ctrl->fail[w] >> lane) & 1u);
+            const bool over = (ctrl->gflag[w] >> lane) & 1u;
+            ctrl->it[s] = it;
+            if (it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over) atomicOr(&ctrl->fin[trip & 1], 1u << s);
+        }
+    }
+    __syncthreads();
+    const uint32_t fin = ctrl->fin[trip & 1];
+    if (tid < W) { ctrl->failed[tid] = ctrl->fail[tid]; ctrl->fail[tid] = 0u; ctrl->fresh[tid] = 0u; }
+    if (tid == 0) ctrl->fin[(trip + 1) & 1] = 0u;
+    ++trip;
+    if (fin) __syncthreads();  // the finish code reads what the threads above just wrote
+    return fin;
+}
+
+// ------------------------------------------------------------------------------------------
 // the kernel
 //   DC   largest check degree, REG: every check has degree DC
 //   DV   largest variable degree with an exact body
 //   NI   word sets per thread in the check / syndrome phases (W is a multiple of NI)
 //   M, N compile-time m and n of the named codes (0 = read them from the parameters)
-//   MAXT, NCTA  launch bounds: CTA size and co-resident CTAs per SM.  Two CTAs drift out of phase, so
+//   MAXT, NCTA  launch bounds: CTA size and co-resident CTAs per SM.  Co-resident CTAs drift out of phase, so
 //        one's latency-bound variable phase overlaps the other's ALU-bound check phase.
+//   IPT  0: separate syndrome pass (any number of check items per thread);
+//        > 0: fused schedule -- every thread keeps the forward results of its <= IPT check items in registers,
+//        the syndrome falls out of the forward pass, the stop decision and the refill happen between the
+//        forward and the backward pass, and no word is read a third time.  Needs items <= IPT * threads.
 // ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N>
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int IPT>
 __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -611,7 +850,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
     const int n = N ? N : p.n, m = M ? M : p.m, E = M ? DC * M : p.E, W = p.W;
     uint32_t *edge = smem;                 // [W][E]
     uint32_t *llr = edge + (size_t)W * E;  // [W][n]
-    uint32_t *cxor = llr + (size_t)W * n;  // [W][m] inverted XOR of every check's incoming words
+    uint32_t *cxor = llr + (size_t)W * n;  // [W][m] inverted XOR of every check's incoming words (IPT == 0)
     Ctrl *ctrl = reinterpret_cast<Ctrl *>(cxor + (size_t)W * m);
     // degree tables next to the control block (irregular codes dispatch on them once per node and phase)
     constexpr bool REGV = PREFETCH_VEDGE && M != 0 && REG && DV <= 8;
@@ -629,8 +868,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
     __syncthreads();
     unsigned int trip = 0;
 
-    uint32_t fin = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);  // slots to (re)fill
-    bool first = true;
+    const uint32_t all_slots = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);
     const int items = (W / NI) * m;  // (word-set group, check)
 #ifdef LDPC_PHASE_TIMING
     long long t_phase[5] = {0, 0, 0, 0, 0}, t_mark = clock64();
@@ -639,142 +877,111 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
 #define LDPC_MARK(k) do { } while (0)
 #endif
 
+    if (IPT > 0) {
+        // ============================================================ fused schedule
+        CheckState<DC, NI> st[IPT > 0 ? IPT : 1];
+        bool first = true;
+        for (;;) {
+            // ---- forward pass + syndrome of the state the last variable phase left
+            uint32_t mine[NI];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) mine[j] = 0u;
+#pragma unroll
+            for (int q = 0; q < IPT; ++q) {
+                const int i = tid + q * nthreads;
+                if (i < items) {
+                    const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
+                    const uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
+                    if (REG) {
+                        check_forward<T, DC, DC, NI>(e0, m, E, st[q]);
+                    } else {
+                        const int d = cdeg_s[c];
+                        LDPC_DEGREE_SWITCH(d, DC, (check_forward<T, D, DC, NI>(e0, m, E, st[q])))
+                    }
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) {
+                        const uint32_t fb = T::fail_bits(st[q].acc[j]);
+                        if (W == NI) mine[j] |= fb;
+                        else if (fb) atomicOr(&ctrl->fail[wg * NI + j], fb);
+                    }
+                }
+            }
+            if (W == NI) {
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    const uint32_t r = __reduce_or_sync(0xffffffffu, mine[j]);
+                    if (lane_id == 0 && r) atomicOr(&ctrl->fail[j], r);
+                }
+            }
+            __syncthreads();
+            LDPC_MARK(3);
+
+            // ---- stop decision, results, refill
+            uint32_t fin = bookkeeping<T>(p, ctrl, W, trip);
+            if (first) fin = all_slots;
+            if (fin) {
+                const int active = finish_and_refill<T, DC, REG, REGV>(p, ctrl, edge, llr, cdeg_s, vdeg_s, fin, first, n, m, E, W, frames);
+                if (active == 0) break;
+                first = false;
+                // a refilled lane starts from zeros: redo the forward pass of the checks in the word sets it touched
+#pragma unroll
+                for (int q = 0; q < IPT; ++q) {
+                    const int i = tid + q * nthreads;
+                    if (i < items) {
+                        const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
+                        uint32_t touched = 0;
+#pragma unroll
+                        for (int j = 0; j < NI; ++j) touched |= ctrl->fresh[wg * NI + j];
+                        if (touched) {
+                            const uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
+                            if (REG) {
+                                check_forward<T, DC, DC, NI>(e0, m, E, st[q]);
+                            } else {
+                                const int d = cdeg_s[c];
+                                LDPC_DEGREE_SWITCH(d, DC, (check_forward<T, D, DC, NI>(e0, m, E, st[q])))
+                            }
+                        }
+                    }
+                }
+            }
+            LDPC_MARK(0);
+
+            // ---- backward pass + write-back
+#pragma unroll
+            for (int q = 0; q < IPT; ++q) {
+                const int i = tid + q * nthreads;
+                if (i < items) {
+                    const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
+                    uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
+                    if (REG) {
+                        check_backward<T, DC, DC, NI>(e0, m, E, st[q]);
+                    } else {
+                        const int d = cdeg_s[c];
+                        LDPC_DEGREE_SWITCH(d, DC, (check_backward<T, D, DC, NI>(e0, m, E, st[q])))
+                    }
+                }
+            }
+            __syncthreads();
+            LDPC_MARK(1);
+
+            // ---- variable phase
+            if (p.post) variable_phase<T, DV, true, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
+            else variable_phase<T, DV, false, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
+            __syncthreads();
+            LDPC_MARK(2);
+        }
+    } else {
+    // ================================================================ schedule with a separate syndrome pass
+    uint32_t fin = all_slots;  // slots to (re)fill
+    bool first = true;
     for (;;) {
         // ---------------------------------------------------------------- finish + refill
         if (fin) {
-            if (!first) {
-                // results of the frames that stop now (smem state == after their last variable phase)
-                for (int s = 0; s < nslots; ++s) {
-                    if (!((fin >> s) & 1u)) continue;
-                    const int w = s / T::LANES, lane = s % T::LANES;
-                    const int f = ctrl->fid[s];
-                    const bool overflow = (ctrl->gflag[w] >> lane) & 1u;
-                    if (tid == 0)
-                        p.iters[f] = overflow ? -1 : (p.max_iter == 0 ? (int)((ctrl->failed[w] >> lane) & 1u) : ctrl->it[s]);
-                    const uint32_t *ew = edge + (size_t)w * E;
-                    const bool count_errors = p.mc_mode != 0 && !overflow;
-                    if (p.bits || count_errors) {
-                        unsigned int errs = 0;
-                        for (int v0 = 0; v0 < n; v0 += nthreads) {
-                            const int v = v0 + tid;
-                            uint32_t b = 0;
-                            if (v < n) {
-                                if (REGV || vdeg_s[v]) b = T::hd_bit(ew[p.vedge[v]], lane);
-                                else b = T::lane_value(llr[(size_t)w * n + v], lane) <= 0;
-                            }
-                            const uint32_t word = __ballot_sync(0xffffffffu, b);
-                            if (lane_id == 0 && v < n) {
-                                if (p.bits) p.bits[(size_t)f * p.nw32 + (v >> 5)] = word;
-                                if (count_errors) {
-                                    const uint32_t sent = p.mc_cw ? p.mc_cw[(size_t)f * p.mc_cw_stride + (v >> 5)] : 0u;
-                                    const uint32_t mask = p.mc_info ? p.mc_info[v >> 5] : 0xffffffffu;
-                                    errs += __popc((word ^ sent) & mask);
-                                }
-                            }
-                        }
-                        if (count_errors) {
-                            if (tid == 0) ctrl->errs = 0u;
-                            __syncthreads();
-                            if (errs) atomicAdd(&ctrl->errs, errs);
-                            __syncthreads();
-                            if (tid == 0) {
-                                const unsigned int e = ctrl->errs;
-                                if (p.mc_frame_err) p.mc_frame_err[f] = (unsigned short)min(e, 65535u);
-                                atomicAdd(&p.mc_counters[0], 1ull);
-                                if (e) atomicAdd(&p.mc_counters[1], 1ull);
-                                if (e) atomicAdd(&p.mc_counters[2], (unsigned long long)e);
-                                atomicAdd(&p.mc_counters[3], (unsigned long long)ctrl->it[s]);
-                            }
-                        }
-                    }
-                    if (p.v2c) {
-                        int *out = p.v2c + (size_t)f * p.dc_max * m;
-                        for (int i = tid; i < p.dc_max * m; i += nthreads) {
-                            const int k = i / m, c = i - k * m;
-                            out[i] = k < (REG ? DC : (int)cdeg_s[c]) ? T::v2c_value(ew[i], lane) : 0;
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-            if (tid == 0) {
-                for (int s = 0; s < nslots; ++s) {
-                    if (!((fin >> s) & 1u)) continue;
-                    const int w = s / T::LANES, lane = s % T::LANES;
-                    const unsigned long long f = atomicAdd(p.queue, 1ull);
-                    ctrl->fid[s] = f < (unsigned long long)frames ? (p.index ? p.index[f] : (int)f) : -1;
-                    if (p.mc_mode == 2 && ctrl->fid[s] >= 0)
-                        ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed,
-                                                     lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)ctrl->fid[s]));
-                    ctrl->it[s] = 0;
-                    ctrl->fresh[w] |= 1u << lane;
-                    ctrl->gflag[w] &= ~(1u << lane);
-                }
-            }
-            __syncthreads();
-            for (int s = 0; s < nslots; ++s) {
-                if (!((fin >> s) & 1u)) continue;
-                const int w = s / T::LANES, lane = s % T::LANES;
-                const int f = ctrl->fid[s];
-                // a new frame starts from all-zero messages: the check phase maps zeros to zeros and the variable
-                // phase then produces post = LLR, v2c = LLR, which is the reference's initialisation (:45-61)
-                if (T::LANES == 1) {
-                    if (!first) for (int i = tid; i < E; i += nthreads) edge[(size_t)w * E + i] = 0u;
-                } else {
-                    const uint32_t keep = ~T::lane_mask(lane);
-                    if (!first) for (int i = tid; i < E; i += nthreads) edge[(size_t)w * E + i] &= keep;
-                }
-                bool any_bad = false;
-                if (p.mc_mode == 1 && f >= 0) {
-                    const unsigned long long g = p.mc_first + (unsigned long long)f;
-                    for (int q = tid; 4 * q < n; q += nthreads) {
-                        float z[4];
-                        philox_normals(p, g, (uint32_t)q, z);
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const int v = 4 * q + h;
-                            if (v < n) {
-                                bool bad;
-                                uint32_t *dst = &llr[(size_t)w * n + v];
-                                *dst = T::set_lane(*dst, lane, quantise_llr(p, (double)z[h], cw_bit(p, f, v)), bad);
-                                any_bad |= bad;
-                            }
-                        }
-                    }
-                } else {
-                    for (int v = tid; v < n; v += nthreads) {
-                        int val = 0;
-                        if (f >= 0) {
-                            if (p.mc_mode == 2)
-                                val = quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], p.mc_pow[v])), cw_bit(p, f, v));
-                            else
-                                val = p.llr_bits == 16 ? (int)reinterpret_cast<const int16_t *>(p.llr)[(size_t)f * n + v]
-                                                       : reinterpret_cast<const int *>(p.llr)[(size_t)f * n + v];
-                        }
-                        bool bad;
-                        uint32_t *dst = &llr[(size_t)w * n + v];
-                        *dst = T::set_lane(*dst, lane, val, bad);
-                        any_bad |= bad;
-                    }
-                }
-                if (p.mc_mode != 0 && p.mc_pin_count > 0 && f >= 0) {
-                    __syncthreads();
-                    for (int i = tid; i < p.mc_pin_count; i += nthreads) {
-                        bool bad;
-                        uint32_t *dst = &llr[(size_t)w * n + p.mc_pin[i]];
-                        *dst = T::set_lane(*dst, lane, p.mc_pin_value, bad);
-                    }
-                }
-                if (any_bad) atomicOr(&ctrl->gflag[w], 1u << lane);
-            }
-            __syncthreads();
-            int active = 0;
-            for (int s = 0; s < nslots; ++s) active += ctrl->fid[s] >= 0;
+            const int active = finish_and_refill<T, DC, REG, REGV>(p, ctrl, edge, llr, cdeg_s, vdeg_s, fin, first, n, m, E, W, frames);
             if (active == 0) break;
             first = false;
         }
         LDPC_MARK(0);
-
         // ---------------------------------------------------------------- check phase
         for (int i = tid; i < items; i += nthreads) {
             const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
@@ -890,26 +1097,9 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
         LDPC_MARK(3);
 
         // ---------------------------------------------------------------- bookkeeping
-        // one thread per slot decides; the stop mask travels through shared memory (double buffered by trip
-        // parity so it can be cleared without another barrier)
-        if (tid < nslots) {
-            const int s = tid, w = s / T::LANES, lane = s % T::LANES;
-            if (ctrl->fid[s] >= 0) {
-                const bool fresh = (ctrl->fresh[w] >> lane) & 1u;
-                const int it = ctrl->it[s] + (fresh ? 0 : 1);
-                const bool pass = !((ctrl->fail[w] >> lane) & 1u);
-                const bool over = (ctrl->gflag[w] >> lane) & 1u;
-                ctrl->it[s] = it;
-                if (it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over) atomicOr(&ctrl->fin[trip & 1], 1u << s);
-            }
-        }
-        __syncthreads();
-        fin = ctrl->fin[trip & 1];
-        if (tid < W) { ctrl->failed[tid] = ctrl->fail[tid]; ctrl->fail[tid] = 0u; ctrl->fresh[tid] = 0u; }
-        if (tid == 0) ctrl->fin[(trip + 1) & 1] = 0u;
-        ++trip;
-        if (fin) __syncthreads();  // the finish code reads what the threads above just wrote
+        fin = bookkeeping<T>(p, ctrl, W, trip);
         LDPC_MARK(4);
+    }
     }
 #ifdef LDPC_PHASE_TIMING
     if (tid == 0 && blockIdx.x == 0)
