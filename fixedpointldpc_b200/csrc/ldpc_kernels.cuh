@@ -213,7 +213,7 @@ struct Packed16 {
     template <int D> __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd)
     {
         int lo = a.lo, hi = a.hi;
-        // D <= 2: |post| <= 2^13-1 + 2*(2^13+9) fits the lane, and a wrapped post + (-c2v) still trips the guard
+        // D <= 2: |post| <= LLR_LIMIT-1 + 2*(2^13+19) and |post + (-c2v)| stay below 2^15 (see LLR_LIMIT)
         if (D > 2) { lo = max(min(lo, CLAMP), -CLAMP); hi = max(min(hi, CLAMP), -CLAMP); }
         const uint32_t pw = __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
         hd = (__vadd2(pw, 0xffffffffu) >> 1) & HD;  // sign of post-1 per lane, moved to bit 14
@@ -242,9 +242,13 @@ struct Packed16 {
         return (h & 0x8000u) ? -mag : mag;
     }
     __device__ static __forceinline__ uint32_t hd_bit(uint32_t w, int lane) { return (w >> (lane ? 30 : 14)) & 1u; }
+    // Channel values are admitted below LLR_LIMIT, slightly under 2^13, so that the unclamped posterior of a
+    // degree <= 2 variable cannot wrap its lane: LLR_LIMIT-1 + 2*C2V_MAX + C2V_MAX < 2^15, where
+    // C2V_MAX = 2^13-1 + 20 bounds every check output (each sxor adds at most 10 to the smaller magnitude).
+    static constexpr int LLR_LIMIT = 8100;
     __device__ static __forceinline__ uint32_t set_lane(uint32_t old, int lane, int val, bool &bad)
     {
-        bad = (uint32_t)(val + LIMIT) >= 2u * LIMIT;
+        bad = (uint32_t)(val + LLR_LIMIT - 1) >= 2u * LLR_LIMIT - 1u;  // |val| >= LLR_LIMIT
         uint32_t h = (uint32_t)val & 0xffffu;
         return lane ? ((old & 0x0000ffffu) | (h << 16)) : ((old & 0xffff0000u) | h);
     }

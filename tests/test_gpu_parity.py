@@ -216,3 +216,46 @@ def test_full_size_properties(fp, po):
     assert (d_iters.cpu().numpy() == out["iters"]).all()
     assert (d_bits.cpu().numpy().view(np.uint32) == out["bits"]).all()
     dec.close()
+
+
+@pytest.mark.parametrize("name", ["wifi", "a5", "c79"])
+def test_guard_boundary_values(fp, po, name):
+    """Channel values and messages right at the packed kernel's range limits (8100 for LLRs, 2^13 for messages,
+    the +-24000 posterior clamp): auto precision must stay bit exact, whichever kernel ends up decoding a frame."""
+    code = fp.codes.NAMED[name]()
+    t = tables_of(code)
+    orc = po.Oracle(t)
+    rng = np.random.default_rng(13)
+    frames = 40
+    llr = rng.integers(-8200, 8201, size=(frames, code.n)).astype(np.int32)
+    llr[0] = 8099; llr[1] = -8099; llr[2] = 8100; llr[3] = -8100; llr[4] = 8191; llr[5] = -8192
+    llr[6] = rng.choice(np.array([8099, -8099, 8100, -8100], np.int32), size=code.n)
+    llr[7:20] = rng.integers(-2100, 2101, size=(13, code.n))       # grows past 2^13 while decoding (dv up to 11)
+    llr[20:30] = np.abs(rng.integers(1500, 8099, size=(10, code.n)))  # all positive: posteriors pile up -> clamp
+    want = _expect(orc, llr, False)
+    dec = fp.Decoder(code, precision=0)
+    out = dec.decode(llr, want_post=True, want_v2c=True)
+    _compare(fp, code, t, out, want)
+    st = dec.stats()
+    assert 0 < st["fallback_frames"] <= frames
+    dec.close()
+
+
+@pytest.mark.parametrize("name,snr_db,frames,scale", [("wifi", 1.5, 1 << 16, 1), ("a5", 3.8, 1 << 15, 1), ("c79", 3.2, 1 << 15, 1),
+                                                      ("a24", 4.5, 1 << 11, 1), ("wifi", 2.0, 1 << 14, 6), ("a5", 4.0, 1 << 13, 5)])
+def test_packed_kernel_equals_int32_kernel_at_scale(fp, name, snr_db, frames, scale):
+    """The int16x2 kernel (+ guard fallback) against the exact int32 kernel on tens of thousands of frames:
+    every iteration count and every decoded bit must agree (the int32 kernel itself is pinned to the oracle above)."""
+    code = fp.codes.NAMED[name]()
+    rate = fp.codes.INFO_BITS[name] / code.n
+    llr = channel_frames(code.n, rate, snr_db, frames, seed=frames + scale) * scale
+    d_auto = fp.Decoder(code, precision=0, precheck=(name in ("a5", "a24")))
+    d_32 = fp.Decoder(code, precision=32, precheck=(name in ("a5", "a24")))
+    a = d_auto.decode(llr)
+    b = d_32.decode(llr)
+    assert (a["iters"] == b["iters"]).all()
+    assert (a["bits"] == b["bits"]).all()
+    assert len(np.unique(a["iters"])) > 3
+    if scale > 1:
+        assert d_auto.stats()["fallback_frames"] > 0
+    d_auto.close(); d_32.close()
