@@ -242,7 +242,7 @@ def test_guard_boundary_values(fp, po, name):
 
 
 @pytest.mark.parametrize("name,snr_db,frames,scale", [("wifi", 1.5, 1 << 16, 1), ("a5", 3.8, 1 << 15, 1), ("c79", 3.2, 1 << 15, 1),
-                                                      ("a24", 4.5, 1 << 11, 1), ("wifi", 2.0, 1 << 14, 6), ("a5", 4.0, 1 << 13, 5)])
+                                                      ("a24", 5.6, 1 << 11, 1), ("wifi", 2.0, 1 << 14, 6), ("a5", 4.0, 1 << 13, 5)])
 def test_packed_kernel_equals_int32_kernel_at_scale(fp, name, snr_db, frames, scale):
     """The int16x2 kernel (+ guard fallback) against the exact int32 kernel on tens of thousands of frames:
     every iteration count and every decoded bit must agree (the int32 kernel itself is pinned to the oracle above)."""
