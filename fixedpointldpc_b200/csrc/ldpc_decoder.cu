@@ -69,7 +69,7 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 5 && c.m == 235 && c.n == 2209)          // array p47 r5
         return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209, 1>();
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 24 && c.m == 1128 && c.n == 2209)
-        return make_choice<T, 47, true, 24, 1, 768, 1, 1128, 2209, 0>();   // array p47 r24
+        return make_choice<T, 47, true, 24, 1, 576, 1, 1128, 2209, 2>();   // array p47 r24 (two checks per thread)
     if (regular && vregular && c.dc_max == 28 && c.dv_max == 4 && c.m == 316 && c.n == 2212)          // cut79
         return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212, 1>();
     if (c.dc_max == 8 && c.dv_max <= 12 && c.m == 972 && c.n == 1944)                                // 802.11n 1944 r1/2
