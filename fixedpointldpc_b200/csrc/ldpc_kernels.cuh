@@ -184,7 +184,7 @@ struct Packed16 {
         uint32_t x = 4u * mn + ud;               // 4*(mn + u(diff)), lanes < 2^16
         // x - us on the FMA pipe (the ALU pipe is the bound resource); every lane stays >= 0
         asm("mad.lo.u32 %0, %1, 0xffffffff, %0;" : "+r"(x) : "r"(us));
-        return x >> 2;                           // low two bits of every lane are zero
+        return x >> 2;  // low two bits of every lane are zero (IMAD.HI here, 2 FMA slots for 1 ALU slot, measured slower)
     }
     __device__ static __forceinline__ uint32_t neg_c2v(uint32_t o, uint32_t inv)
     {
@@ -574,8 +574,7 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
             for (int j = 0; j < DV; ++j) next[j] = vn < n ? (uint32_t)p.vedge[j * n + vn] * 4u : 0u;
             variable_node<T, DV, POST>(p, ctrl, edge, llr, v, W, n, E, off);
         }
-        return;
-    }
+    } else
     for (int v = threadIdx.x; v < n; v += blockDim.x) {
         const int dv = vdeg[v];
         bool done = false;
