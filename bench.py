@@ -133,6 +133,17 @@ def _cpu_worker(args):
     return dt, iters
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_decode(code_name, code, llr_host, cores):
     """Decode llr_host [frames][n] int32 on `cores` processes; returns (seconds, iters, kind)."""
     import multiprocessing as mp
@@ -182,7 +193,7 @@ def run_reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": name, "ebn0_db": ebn0, "frames_per_step": frames,
                    "avg_iters": total_it / (frames * args.steps)},
-        "cpu_baseline": {"value": value, "unit": "Gbit/s", "cores": cores, "kind": kind,
+        "cpu_baseline": {"value": value, "unit": "Gbit/s", "cores": cores, "kind": kind, "cpu": cpu_model(),
                          "sample": "%d frames per step (%d per core), same channel as the GPU arm" % (frames, per_core),
                          "frames_per_s": frames * args.steps / t},
         "e2e": {"value": value, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -313,10 +324,12 @@ def run_gpu_arm(args):
     algo_bytes = 2 * code.n + (code.n + 7) // 8 + 4  # int16 LLR in + packed bits + iteration count out
     per_gpu_fps = fps / world
     achieved = per_gpu_fps * algo_bytes / 1e9
-    traffic = None  # DRAM bytes per launch from the committed ncu capture (profiles/r01/traffic.json)
+    traffic, ncu = None, None  # DRAM bytes per launch / pipe utilisation from the committed ncu capture
     try:
         with open(os.path.join(ROOT, "profiles", "r01", "traffic.json")) as fh:
-            traffic = json.load(fh)[args.code]["dram_bytes_per_frame"] * frames
+            cap = json.load(fh)[args.code]
+        traffic = cap["dram_bytes_per_frame"] * frames
+        ncu = {k: cap[k] for k in ("alu_pipe_pct", "fma_pipe_pct", "lsu_pipe_pct", "issue_per_cycle", "source") if k in cap}
     except Exception:
         pass
     # algorithmic integer work: 18 ops per necessary sxor, 3 per edge, 1 per variable
@@ -345,7 +358,8 @@ def run_gpu_arm(args):
                      "note": "state is smem-resident; the binding resource is integer issue, see roofline_int"},
         "roofline_int": {"bound": "int32 issue slots (ALU+FMA pipes)", "achieved": int_ach, "peak": int_peak,
                          "unit": "Tops/s", "frac": int_ach / int_peak, "algorithmic_ops_per_frame_iter": ops_iter,
-                         "peak_source": "148 SMs x 128 lanes x median SM clock under load (pipes.cu: 64 ALU + 64 FMA lanes/clk/SM)"},
+                         "peak_source": "148 SMs x 128 lanes x median SM clock under load (pipes.cu: 64 ALU + 64 FMA lanes/clk/SM)",
+                         "ncu_bound_resource": ncu},
         "e2e": {"value": e2e_value, "unit": "Gbit/s", "h2d_bytes_per_step": e2e_frames * code.n * 4,
                 "d2h_bytes_per_step": e2e_frames * (4 + code.nw32 * 4), "frames_per_step": e2e_frames,
                 "api": "ldpc_decode_batch (host int32 LLR in, iters + packed bits out)"},
@@ -360,6 +374,7 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         gpu_iters = iters[:sample].cpu().numpy()
         line["cpu_baseline"] = {"value": sample * k / wall / 1e9, "unit": "Gbit/s", "cores": cores, "kind": kind,
+                                "cpu": cpu_model(),
                                 "sample": "first %d frames of the step's batch, one process per core" % sample,
                                 "frames_per_s": sample / wall,
                                 "iteration_count_mismatches_vs_gpu": int((gpu_iters != cpu_iters).sum())}

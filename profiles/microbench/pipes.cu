@@ -47,6 +47,11 @@ DEF_KERNEL(mix_min_imad,  asm volatile("min.u16x2 %0, %0, %1; mad.lo.u32 %0, %0,
 DEF_KERNEL(mix_lop_imadhi,asm volatile("lop3.b32 %0, %0, %1, %2, 0x96; mad.hi.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(z)))
 DEF_KERNEL(mix_2lop_imad, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96; lop3.b32 %0, %0, %2, %1, 0xe8; mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(z)))
 DEF_KERNEL(mix_lop_2imad, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96; mad.lo.u32 %0, %0, %1, %2; mad.lo.u32 %0, %0, %2, %1;" : "+r"(x) : "r"(y), "r"(z)))
+DEF_KERNEL(hmnmx2,  ASM1("min.f16x2 %0, %0, %1;"))
+DEF_KERNEL(mix_lop_hmnmx2, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96; min.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y), "r"(z)))
+DEF_KERNEL(mix_vmin_hmnmx2, asm volatile("min.u16x2 %0, %0, %2; min.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y), "r"(z)))
+DEF_KERNEL(hadd2,   ASM1("add.f16x2 %0, %0, %1;"))
+DEF_KERNEL(mix_lop_hadd2, asm volatile("lop3.b32 %0, %0, %1, %2, 0x96; add.f16x2 %0, %0, %1;" : "+r"(x) : "r"(y), "r"(z)))
 DEF_KERNEL(mix_min_dp2a,  { asm volatile("min.u16x2 %0, %0, %1;" : "+r"(x) : "r"(y)); x = (uint32_t)__dp2a_lo((int)x, (int)y, (int)z); })
 
 // g(a,b) candidates: x = chain value, y = message magnitude (packed 16x2, two frames per register)
@@ -131,6 +136,7 @@ int main() {
     RUN(iadd3, 1); RUN(lop3, 1); RUN(shf, 1); RUN(shr, 2); RUN(vminu2, 1); RUN(vadd2, 1); RUN(viaddmax, 1); RUN(vimax3, 1);
     RUN(imnmx, 1); RUN(prmt, 1); RUN(imad, 1); RUN(imadhi, 1); RUN(dp2a, 1); RUN(dp4a, 1);
     RUN(mix_lop_imad, 2); RUN(mix_min_imad, 2); RUN(mix_lop_imadhi, 2); RUN(mix_2lop_imad, 3); RUN(mix_lop_2imad, 3); RUN(mix_min_dp2a, 2);
+    RUN(hmnmx2, 1); RUN(mix_lop_hmnmx2, 2); RUN(mix_vmin_hmnmx2, 2); RUN(hadd2, 1); RUN(mix_lop_hadd2, 2);
     RUN(g_packed_alu, 1); RUN(g_packed_mix, 1); RUN(g_scalar, 1); RUN(g_scalar_dp, 1);
     RUN(lds, 1);
     return 0;
