@@ -232,6 +232,12 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     const int lanes = which == 0 ? 2 : 1;
     const long long slots = (long long)pl.W * lanes;
     int grid = (int)std::min<long long>((long long)d.sm_count * pl.kernel.ctas_per_sm, (frames + slots - 1) / slots);
+    p.has_deg0 = 0;
+    for (int v = 0; v < c.n; ++v) p.has_deg0 |= (c.vdeg[v] == 0);
+    // Slots take their next frame from the queue one frame early (hides the atomic and lets the channel values be
+    // prefetched into L2); with a short queue that would starve the CTAs that start last.  The length of an
+    // indirect queue (re-decode list) is only known on the device.
+    p.claim_ahead = (!count && frames >= 4 * slots * grid) ? 1 : 0;
     CUDA_TRY(cudaMemsetAsync(p.queue, 0, sizeof(unsigned long long), st));
     pl.kernel.fn<<<grid, pl.threads, pl.smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());

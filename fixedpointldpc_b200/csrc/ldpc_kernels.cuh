@@ -43,6 +43,8 @@ struct KParams {
     int max_iter;  // MAX_ITER; 0 = hard decision + syndrome only (iters output: 0 pass, 1 fail)
     uint32_t inv_m;  // floor(2^32 / m) + 1: i / m == umulhi(i, inv_m) for i < 2^16
     int precheck;  // decode_fixpoint's hardDecision pre-check
+    int has_deg0;  // some variable takes part in no check (its hard decision comes from the channel word)
+    int claim_ahead;  // every slot takes its next frame index one frame early (long queues only)
     // io
     const void *llr;  // [frames][n] int32 or int16
     int llr_bits;
@@ -154,11 +156,18 @@ struct Scalar32 {
         return (w & SIGN) ? -mag : mag;
     }
     __device__ static __forceinline__ uint32_t hd_bit(uint32_t w, int) { return (w >> 30) & 1u; }
-    __device__ static __forceinline__ uint32_t set_lane(uint32_t, int, int val, bool &bad)
+    // lane content of a channel word / of a fresh frame's message word: v2c(0) = channel value
+    // (ArrayLDPC_Decoder.cpp:45-61), carrying that value's hard decision
+    __device__ static __forceinline__ uint32_t llr_lane(int val, bool &bad)
     {
         bad = false;
         return (uint32_t)val;
     }
+    __device__ static __forceinline__ uint32_t init_lane(int val)
+    {
+        return (uint32_t)abs(val) | ((uint32_t)val & SIGN) | (val <= 0 ? HD : 0u);
+    }
+    __device__ static __forceinline__ void store_lane(uint32_t *word, int, uint32_t x) { *word = x; }
 };
 
 // Two frames per word (int16x2).  Exact as long as every |LLR|, |posterior| and |message| stays
@@ -246,11 +255,20 @@ struct Packed16 {
     // degree <= 2 variable cannot wrap its lane: LLR_LIMIT-1 + 2*C2V_MAX + C2V_MAX < 2^15, where
     // C2V_MAX = 2^13-1 + 20 bounds every check output (each sxor adds at most 10 to the smaller magnitude).
     static constexpr int LLR_LIMIT = 8100;
-    __device__ static __forceinline__ uint32_t set_lane(uint32_t old, int lane, int val, bool &bad)
+    __device__ static __forceinline__ uint32_t llr_lane(int val, bool &bad)
     {
         bad = (uint32_t)(val + LLR_LIMIT - 1) >= 2u * LLR_LIMIT - 1u;  // |val| >= LLR_LIMIT
-        uint32_t h = (uint32_t)val & 0xffffu;
-        return lane ? ((old & 0x0000ffffu) | (h << 16)) : ((old & 0xffff0000u) | h);
+        return (uint32_t)val & 0xffffu;
+    }
+    __device__ static __forceinline__ uint32_t init_lane(int val)
+    {
+        // a value outside the guard range was flagged when it was loaded; only its low 14 magnitude bits are kept here
+        return ((uint32_t)abs(val) & 0x3fffu) | (val < 0 ? 0x8000u : 0u) | (val <= 0 ? 0x4000u : 0u);
+    }
+    // a lane is a 16-bit half of the word: no read-modify-write
+    __device__ static __forceinline__ void store_lane(uint32_t *word, int lane, uint32_t x)
+    {
+        reinterpret_cast<uint16_t *>(word)[lane] = (uint16_t)x;
     }
 };
 
@@ -356,9 +374,11 @@ struct Ctrl {
     uint32_t gflag[MAX_W];  // per word set: lanes that left the guard range (Packed16)
     uint32_t failed[MAX_W]; // copy of `fail` from the last bookkeeping step, read by the finish code
     int fid[MAX_SLOTS];     // frame index decoded in the slot, -1 = idle
+    int next[MAX_SLOTS];    // frame the slot decodes after this one (taken from the queue one frame early), -1 = none
+    int newfid[MAX_SLOTS];  // frame moving into the slot during a refill
     int it[MAX_SLOTS];      // iterations completed by that frame
     uint32_t lehmer[MAX_SLOTS];  // Lehmer state before the slot's frame (MC mode 2)
-    unsigned int errs;      // info-bit errors of the frame being finished (MC mode)
+    unsigned int errs[MAX_SLOTS];  // info-bit errors of the frames being finished (MC mode)
     uint32_t fin[2];        // slots that stop, written in the bookkeeping step; indexed by loop-trip parity
 };
 
@@ -662,62 +682,138 @@ __device__ __forceinline__ void check_backward(uint32_t *e0, int m, int wstride,
     }
 
 // ------------------------------------------------------------------------------------------
-// results of the slots in `fin` (unless `first`), then refill them from the frame queue.
-// Returns the number of active slots.  Called by every thread of the CTA (contains barriers).
+// refill
 // ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG, bool REGV>
+__device__ __forceinline__ void prefetch_l2(const void *ptr)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
+// One pass over the variables for the slots in `fin`, thread per variable:
+//   emit  the hard decisions of the frame that leaves the slot (ballot over 32 consecutive variables): packed
+//         bits and / or the error count of Monte-Carlo mode
+//   fill  the frame that moves in: its channel word and the message words of its edges, which start as
+//         v2c(0) = channel value (the reference's initialisation, ArrayLDPC_Decoder.cpp:45-61).  A lane is a
+//         16-bit half of its word (Packed16), so these are plain stores.
+// `from_smem`: the channel values were generated into the channel words already (Monte-Carlo mode); otherwise
+// they are read from global memory, UNR loads in flight per thread.  A thread reads the old hard decision of a
+// variable before it overwrites that variable's words, and nobody else touches them: no barrier in between.
+template <class T, int DV, bool REGV>
+__device__ __forceinline__ void fill_pass(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr, const uint8_t *vdeg_s,
+                                          uint32_t fin, bool emit, bool fill, bool from_smem, int n, int E)
+{
+    constexpr int UNR = 4;
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
+    uint32_t bad_slots = 0;
+    for (uint32_t left = fin; left; left &= left - 1u) {
+        const int s = __ffs(left) - 1;
+        const int w = s / T::LANES, lane = s % T::LANES;
+        const int fo = emit ? ctrl->fid[s] : -1, fn = ctrl->newfid[s];
+        uint32_t *ew = edge + (size_t)w * E, *lw = llr + (size_t)w * n;
+        const int16_t *g16 = reinterpret_cast<const int16_t *>(p.llr) + (size_t)(fn >= 0 ? fn : 0) * n;
+        const int *g32 = reinterpret_cast<const int *>(p.llr) + (size_t)(fn >= 0 ? fn : 0) * n;
+        for (int base = 0; base < n; base += UNR * nthreads) {
+            int val[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int v = base + u * nthreads + tid;
+                val[u] = 0;
+                if (fill && v < n) {
+                    if (from_smem) val[u] = T::lane_value(lw[v], lane);
+                    else if (fn >= 0) val[u] = p.llr_bits == 16 ? (int)g16[v] : g32[v];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                if (base + u * nthreads < n) {  // uniform
+                    const int v = base + u * nthreads + tid;
+                    const int dv = v < n ? (REGV ? DV : (int)vdeg_s[v]) : 0;
+                    const uint32_t a0 = dv ? (uint32_t)p.vedge[v] : 0u;
+                    if (fo >= 0) {
+                        uint32_t b = 0;
+                        if (v < n) b = dv ? T::hd_bit(ew[a0], lane) : (uint32_t)(T::lane_value(lw[v], lane) <= 0);
+                        const uint32_t word = __ballot_sync(0xffffffffu, b);
+                        if (lane_id == 0 && v < n) {
+                            if (p.bits) p.bits[(size_t)fo * p.nw32 + (v >> 5)] = word;
+                            if (p.mc_mode != 0) {
+                                const uint32_t sent = p.mc_cw ? p.mc_cw[(size_t)fo * p.mc_cw_stride + (v >> 5)] : 0u;
+                                const uint32_t mask = p.mc_info ? p.mc_info[v >> 5] : 0xffffffffu;
+                                const unsigned int e = __popc((word ^ sent) & mask);
+                                if (e) atomicAdd(&ctrl->errs[s], e);
+                            }
+                        }
+                    }
+                    if (fill && v < n) {
+                        if (!from_smem) {
+                            bool bad;
+                            T::store_lane(&lw[v], lane, T::llr_lane(val[u], bad));
+                            if (bad) bad_slots |= 1u << s;
+                        }
+                        const uint32_t iw = T::init_lane(val[u]);
+                        if (REGV) {
+                            T::store_lane(&ew[a0], lane, iw);
+#pragma unroll
+                            for (int j = 1; j < DV; ++j) T::store_lane(&ew[p.vedge[j * n + v]], lane, iw);
+                        } else {
+#pragma unroll 4
+                            for (int j = 0; j < dv; ++j) T::store_lane(&ew[p.vedge[j * n + v]], lane, iw);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    for (int s = 0; bad_slots; ++s, bad_slots >>= 1)
+        if (bad_slots & 1u) atomicOr(&ctrl->gflag[s / T::LANES], 1u << (s % T::LANES));
+}
+
+// frame index behind queue position q (-1 past the end)
+__device__ __forceinline__ int queue_frame(const KParams &p, unsigned long long q, long long frames)
+{
+    return q < (unsigned long long)frames ? (p.index ? p.index[q] : (int)q) : -1;
+}
+
+// Results of the slots in `fin` (unless `first`), then the next frames move in.  Returns the number of active
+// slots.  Called by every thread of the CTA (contains barriers).
+template <class T, int DC, int DV, bool REG, bool REGV>
 __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
                                                  const uint8_t *cdeg_s, const uint8_t *vdeg_s, uint32_t fin, bool first,
                                                  int n, int m, int E, int W, long long frames)
 {
     const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
     const int nslots = W * T::LANES;
-    if (!first) {
-        // results of the frames that stop now (smem state == after their last variable phase)
-        for (int s = 0; s < nslots; ++s) {
-            if (!((fin >> s) & 1u)) continue;
+    const bool mine = tid < nslots && ((fin >> tid) & 1u);  // one thread per stopping slot (all in warp 0)
+    const bool emit = !first && (p.bits || p.mc_mode != 0);
+    unsigned long long claim = 0;
+    bool was_over = false;
+    int old_it = 0;
+    if (mine) {
+        const int s = tid, w = s / T::LANES, lane = s % T::LANES;
+        was_over = (ctrl->gflag[w] >> lane) & 1u;
+        old_it = ctrl->it[s];
+        if (!first)
+            p.iters[ctrl->fid[s]] = was_over ? -1 : (p.max_iter == 0 ? (int)((ctrl->failed[w] >> lane) & 1u) : old_it);
+        // With claim_ahead the slot's next frame was taken from the queue (and its channel values pulled into L2)
+        // when the previous one moved in; the atomic issued here is for the frame after, and its round trip
+        // overlaps the passes below.
+        claim = atomicAdd(p.queue, 1ull);
+        const int f = p.claim_ahead ? ctrl->next[s] : queue_frame(p, claim, frames);
+        ctrl->newfid[s] = f;
+        if (p.mc_mode == 2 && f >= 0)
+            ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed, lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)f));
+        ctrl->errs[s] = 0u;
+        atomicAnd(&ctrl->gflag[w], ~(1u << lane));
+    }
+    __syncthreads();
+    if (!first && (p.post || p.v2c)) {  // parity mode: state of the stopping frames
+        for (uint32_t left = fin; left; left &= left - 1u) {
+            const int s = __ffs(left) - 1;
             const int w = s / T::LANES, lane = s % T::LANES;
             const int f = ctrl->fid[s];
-            const bool overflow = (ctrl->gflag[w] >> lane) & 1u;
-            if (tid == 0)
-                p.iters[f] = overflow ? -1 : (p.max_iter == 0 ? (int)((ctrl->failed[w] >> lane) & 1u) : ctrl->it[s]);
-            const uint32_t *ew = edge + (size_t)w * E;
-            const bool count_errors = p.mc_mode != 0 && !overflow;
-            if (p.bits || count_errors) {
-                unsigned int errs = 0;
-                for (int v0 = 0; v0 < n; v0 += nthreads) {
-                    const int v = v0 + tid;
-                    uint32_t b = 0;
-                    if (v < n) {
-                        if (REGV || vdeg_s[v]) b = T::hd_bit(ew[p.vedge[v]], lane);
-                        else b = T::lane_value(llr[(size_t)w * n + v], lane) <= 0;
-                    }
-                    const uint32_t word = __ballot_sync(0xffffffffu, b);
-                    if (lane_id == 0 && v < n) {
-                        if (p.bits) p.bits[(size_t)f * p.nw32 + (v >> 5)] = word;
-                        if (count_errors) {
-                            const uint32_t sent = p.mc_cw ? p.mc_cw[(size_t)f * p.mc_cw_stride + (v >> 5)] : 0u;
-                            const uint32_t mask = p.mc_info ? p.mc_info[v >> 5] : 0xffffffffu;
-                            errs += __popc((word ^ sent) & mask);
-                        }
-                    }
-                }
-                if (count_errors) {
-                    if (tid == 0) ctrl->errs = 0u;
-                    __syncthreads();
-                    if (errs) atomicAdd(&ctrl->errs, errs);
-                    __syncthreads();
-                    if (tid == 0) {
-                        const unsigned int e = ctrl->errs;
-                        if (p.mc_frame_err) p.mc_frame_err[f] = (unsigned short)min(e, 65535u);
-                        atomicAdd(&p.mc_counters[0], 1ull);
-                        if (e) atomicAdd(&p.mc_counters[1], 1ull);
-                        if (e) atomicAdd(&p.mc_counters[2], (unsigned long long)e);
-                        atomicAdd(&p.mc_counters[3], (unsigned long long)ctrl->it[s]);
-                    }
-                }
-            }
+            if (p.post && ctrl->it[s] == 0)  // stopped before its first variable phase: posterior == channel value
+                for (int v = tid; v < n; v += nthreads) p.post[(size_t)f * n + v] = T::lane_value(llr[(size_t)w * n + v], lane);
             if (p.v2c) {
+                const uint32_t *ew = edge + (size_t)w * E;
                 int *out = p.v2c + (size_t)f * p.dc_max * m;
                 for (int i = tid; i < p.dc_max * m; i += nthreads) {
                     const int k = i / m, c = i - k * m;
@@ -727,75 +823,99 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
         }
         __syncthreads();
     }
-    if (tid == 0) {
-        for (int s = 0; s < nslots; ++s) {
-            if (!((fin >> s) & 1u)) continue;
-            const int w = s / T::LANES, lane = s % T::LANES;
-            const unsigned long long f = atomicAdd(p.queue, 1ull);
-            ctrl->fid[s] = f < (unsigned long long)frames ? (p.index ? p.index[f] : (int)f) : -1;
-            if (p.mc_mode == 2 && ctrl->fid[s] >= 0)
-                ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed,
-                                             lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)ctrl->fid[s]));
-            ctrl->it[s] = 0;
-            ctrl->fresh[w] |= 1u << lane;
-            ctrl->gflag[w] &= ~(1u << lane);
+    if (p.mc_mode != 0) {
+        // Monte-Carlo mode: the channel values are generated into the channel words first
+        bool emitted = false;
+        if (emit && p.has_deg0) {  // a variable without edges keeps its hard decision in the channel word itself
+            fill_pass<T, DV, REGV>(p, ctrl, edge, llr, vdeg_s, fin, true, false, true, n, E);
+            __syncthreads();
+            emitted = true;
         }
-    }
-    __syncthreads();
-    for (int s = 0; s < nslots; ++s) {
-        if (!((fin >> s) & 1u)) continue;
-        const int w = s / T::LANES, lane = s % T::LANES;
-        const int f = ctrl->fid[s];
-        // a new frame starts from all-zero messages: the check phase maps zeros to zeros and the variable
-        // phase then produces post = LLR, v2c = LLR, which is the reference's initialisation (:45-61)
-        if (T::LANES == 1) {
-            if (!first) for (int i = tid; i < E; i += nthreads) edge[(size_t)w * E + i] = 0u;
-        } else {
-            const uint32_t keep = ~T::lane_mask(lane);
-            if (!first) for (int i = tid; i < E; i += nthreads) edge[(size_t)w * E + i] &= keep;
-        }
-        bool any_bad = false;
-        if (p.mc_mode == 1 && f >= 0) {
-            const unsigned long long g = p.mc_first + (unsigned long long)f;
+        uint32_t bad_slots = 0;
+        if (p.mc_mode == 1) {
             for (int q = tid; 4 * q < n; q += nthreads) {
-                float z[4];
-                philox_normals(p, g, (uint32_t)q, z);
+                for (uint32_t left = fin; left; left &= left - 1u) {
+                    const int s = __ffs(left) - 1;
+                    const int w = s / T::LANES, lane = s % T::LANES;
+                    const int f = ctrl->newfid[s];
+                    float z[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (f >= 0) philox_normals(p, p.mc_first + (unsigned long long)f, (uint32_t)q, z);
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const int v = 4 * q + h;
-                    if (v < n) {
-                        bool bad;
-                        uint32_t *dst = &llr[(size_t)w * n + v];
-                        *dst = T::set_lane(*dst, lane, quantise_llr(p, (double)z[h], cw_bit(p, f, v)), bad);
-                        any_bad |= bad;
+                    for (int h = 0; h < 4; ++h) {
+                        const int v = 4 * q + h;
+                        if (v < n) {
+                            bool bad;
+                            const int val = f >= 0 ? quantise_llr(p, (double)z[h], cw_bit(p, f, v)) : 0;
+                            T::store_lane(&llr[(size_t)w * n + v], lane, T::llr_lane(val, bad));
+                            if (bad) bad_slots |= 1u << s;
+                        }
                     }
                 }
             }
         } else {
             for (int v = tid; v < n; v += nthreads) {
-                int val = 0;
-                if (f >= 0) {
-                    if (p.mc_mode == 2)
-                        val = quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], p.mc_pow[v])), cw_bit(p, f, v));
-                    else
-                        val = p.llr_bits == 16 ? (int)reinterpret_cast<const int16_t *>(p.llr)[(size_t)f * n + v]
-                                               : reinterpret_cast<const int *>(p.llr)[(size_t)f * n + v];
+                const uint32_t pw = p.mc_pow[v];
+                for (uint32_t left = fin; left; left &= left - 1u) {
+                    const int s = __ffs(left) - 1;
+                    const int w = s / T::LANES, lane = s % T::LANES;
+                    const int f = ctrl->newfid[s];
+                    bool bad;
+                    const int val = f >= 0 ? quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], pw)), cw_bit(p, f, v)) : 0;
+                    T::store_lane(&llr[(size_t)w * n + v], lane, T::llr_lane(val, bad));
+                    if (bad) bad_slots |= 1u << s;
                 }
-                bool bad;
-                uint32_t *dst = &llr[(size_t)w * n + v];
-                *dst = T::set_lane(*dst, lane, val, bad);
-                any_bad |= bad;
             }
         }
-        if (p.mc_mode != 0 && p.mc_pin_count > 0 && f >= 0) {
-            __syncthreads();
+        for (int s = 0; bad_slots; ++s, bad_slots >>= 1)
+            if (bad_slots & 1u) atomicOr(&ctrl->gflag[s / T::LANES], 1u << (s % T::LANES));
+        __syncthreads();
+        if (p.mc_pin_count > 0) {  // shortening: known positions pinned (PerfTest.cpp:410-414)
             for (int i = tid; i < p.mc_pin_count; i += nthreads) {
-                bool bad;
-                uint32_t *dst = &llr[(size_t)w * n + p.mc_pin[i]];
-                *dst = T::set_lane(*dst, lane, p.mc_pin_value, bad);
+                const int v = p.mc_pin[i];
+                for (uint32_t left = fin; left; left &= left - 1u) {
+                    const int s = __ffs(left) - 1;
+                    if (ctrl->newfid[s] < 0) continue;
+                    bool bad;
+                    T::store_lane(&llr[(size_t)(s / T::LANES) * n + v], s % T::LANES, T::llr_lane(p.mc_pin_value, bad));
+                }
+            }
+            __syncthreads();
+        }
+        fill_pass<T, DV, REGV>(p, ctrl, edge, llr, vdeg_s, fin, emit && !emitted, true, true, n, E);
+    } else {
+        fill_pass<T, DV, REGV>(p, ctrl, edge, llr, vdeg_s, fin, emit, true, false, n, E);
+    }
+    __syncthreads();
+    int ahead = -1;
+    if (mine) {
+        const int s = tid, w = s / T::LANES, lane = s % T::LANES;
+        if (!first && p.mc_mode != 0 && !was_over) {  // flagged frames are counted by their exact re-decode
+            const unsigned int e = ctrl->errs[s];
+            if (p.mc_frame_err) p.mc_frame_err[ctrl->fid[s]] = (unsigned short)min(e, 65535u);
+            atomicAdd(&p.mc_counters[0], 1ull);
+            if (e) atomicAdd(&p.mc_counters[1], 1ull);
+            if (e) atomicAdd(&p.mc_counters[2], (unsigned long long)e);
+            atomicAdd(&p.mc_counters[3], (unsigned long long)old_it);
+        }
+        ctrl->fid[s] = ctrl->newfid[s];
+        ctrl->it[s] = 0;
+        atomicOr(&ctrl->fresh[w], 1u << lane);
+        if (p.claim_ahead) {
+            ahead = queue_frame(p, claim, frames);
+            ctrl->next[s] = ahead;
+        }
+    }
+    if (p.claim_ahead && p.mc_mode == 0 && tid < 32) {
+        // pull the channel values of the frames just claimed into L2: they are read one frame time from now
+        const size_t bytes = (size_t)n * (p.llr_bits >> 3);
+        for (uint32_t left = fin; left; left &= left - 1u) {
+            const int f = __shfl_sync(0xffffffffu, ahead, __ffs(left) - 1);
+            if (f >= 0) {
+                const char *first_byte = reinterpret_cast<const char *>(p.llr) + (size_t)f * bytes;
+                const char *line = first_byte - (reinterpret_cast<uintptr_t>(first_byte) & 127u) + (size_t)lane_id * 128u;
+                for (; line < first_byte + bytes; line += 32 * 128) prefetch_l2(line);
             }
         }
-        if (any_bad) atomicOr(&ctrl->gflag[w], 1u << lane);
     }
     __syncthreads();
     int active = 0;
@@ -803,7 +923,7 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
     return active;
 }
 
-// stop / continue decision of every slot after the syndrome is known; returns the mask of stopping slots
+// stop / continue decision of every slot after an iteration and its syndrome; returns the mask of stopping slots
 template <class T>
 __device__ __forceinline__ uint32_t bookkeeping(const KParams &p, Ctrl *ctrl, int W, unsigned int &trip)
 {
@@ -813,12 +933,35 @@ __device__ __forceinline__ uint32_t bookkeeping(const KParams &p, Ctrl *ctrl, in
     if (tid < nslots) {
         const int s = tid, w = s / T::LANES, lane = s % T::LANES;
         if (ctrl->fid[s] >= 0) {
-            const bool fresh = (ctrl->fresh[w] >> lane) & 1u;
-            const int it = ctrl->it[s] + (fresh ? 0 : 1);
+            const int it = ctrl->it[s] + 1;
             const bool pass = !((ctrl->fail[w] >> lane) & 1u);
             const bool over = (ctrl->gflag[w] >> lane) & 1u;
             ctrl->it[s] = it;
-            if (it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over) atomicOr(&ctrl->fin[trip & 1], 1u << s);
+            if (it >= p.max_iter || pass || over) atomicOr(&ctrl->fin[trip & 1], 1u << s);
+        }
+    }
+    __syncthreads();
+    const uint32_t fin = ctrl->fin[trip & 1];
+    if (tid < W) { ctrl->failed[tid] = ctrl->fail[tid]; ctrl->fail[tid] = 0u; }
+    if (tid == 0) ctrl->fin[(trip + 1) & 1] = 0u;
+    ++trip;
+    if (fin) __syncthreads();  // the finish code reads what the threads above just wrote
+    return fin;
+}
+
+// the same decision for frames that were just loaded (iteration count 0): decode_fixpoint's pre-check
+// (ArrayLDPC_Decoder.cpp:443-450), the hard-decision-only mode (max_iter == 0) and frames whose channel values
+// already left the packed range.  Clears the `fresh` marks.
+template <class T>
+__device__ __forceinline__ uint32_t bookkeeping_fresh(const KParams &p, Ctrl *ctrl, int W, unsigned int &trip)
+{
+    const int tid = threadIdx.x, nslots = W * T::LANES;
+    if (tid < nslots) {
+        const int s = tid, w = s / T::LANES, lane = s % T::LANES;
+        if (ctrl->fid[s] >= 0 && ((ctrl->fresh[w] >> lane) & 1u)) {
+            const bool pass = !((ctrl->fail[w] >> lane) & 1u);
+            const bool over = (ctrl->gflag[w] >> lane) & 1u;
+            if (p.max_iter == 0 || (pass && p.precheck) || over) atomicOr(&ctrl->fin[trip & 1], 1u << s);
         }
     }
     __syncthreads();
@@ -826,8 +969,143 @@ __device__ __forceinline__ uint32_t bookkeeping(const KParams &p, Ctrl *ctrl, in
     if (tid < W) { ctrl->failed[tid] = ctrl->fail[tid]; ctrl->fail[tid] = 0u; ctrl->fresh[tid] = 0u; }
     if (tid == 0) ctrl->fin[(trip + 1) & 1] = 0u;
     ++trip;
-    if (fin) __syncthreads();  // the finish code reads what the threads above just wrote
+    __syncthreads();
     return fin;
+}
+
+// ------------------------------------------------------------------------------------------
+// syndrome pass (ArrayLDPC_Decoder.cpp:296-333), thread per check and group of NI word sets: XOR of the check's
+// incoming words.  Bit 30/14 is the parity of the hard decisions (the syndrome), bit 31/15 the parity of the
+// signs; the inverted word is kept for the next check phase.  Votes into ctrl->fail.
+// ------------------------------------------------------------------------------------------
+template <class T, int DC, bool REG, int NI>
+__device__ __forceinline__ void syndrome_pass(const KParams &p, Ctrl *ctrl, const uint32_t *edge, uint32_t *cxor,
+                                              const uint8_t *cdeg_s, int items, int m, int E, int W)
+{
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
+    // When the CTA holds a single word-set group (W == NI) every item votes for the same NI word sets: the
+    // thread ORs its items' verdicts in registers and the warp reduces once, after the loop.
+    const bool one_group = (W == NI);
+    uint32_t mine[NI];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) mine[j] = 0u;
+    for (int i0 = tid - lane_id; i0 < items; i0 += nthreads) {
+        const int i = i0 + lane_id;
+        const bool valid = i < items;
+        int wg = 0;
+        uint32_t fb[NI];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) fb[j] = 0u;
+        if (valid) {
+            wg = (int)__umulhi((uint32_t)i, p.inv_m);
+            const int c = i - wg * m;
+            const uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
+            uint32_t acc[NI];
+            if (REG) {
+                check_xors<DC, NI>(e0, m, E, NI, acc);
+            } else {
+                const int d = cdeg_s[c];
+                bool done = false;
+                if (DC <= 16) {
+                    switch (d) {
+#define LDPC_XCASE(D) case D: if (D <= DC) { check_xors<(D <= DC ? D : 2), NI>(e0, m, E, NI, acc); done = true; } break;
+                        LDPC_XCASE(2) LDPC_XCASE(3) LDPC_XCASE(4) LDPC_XCASE(5) LDPC_XCASE(6) LDPC_XCASE(7) LDPC_XCASE(8)
+                        LDPC_XCASE(9) LDPC_XCASE(10) LDPC_XCASE(11) LDPC_XCASE(12) LDPC_XCASE(13) LDPC_XCASE(14)
+                        LDPC_XCASE(15) LDPC_XCASE(16)
+#undef LDPC_XCASE
+                    default: break;
+                    }
+                }
+                if (!done) {
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) {
+                        uint32_t a = 0;
+#pragma unroll
+                        for (int k = 0; k < DC; ++k)
+                            if (k < d) a ^= e0[(size_t)j * E + k * m];
+                        acc[j] = a;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                cxor[(size_t)(wg * NI + j) * m + c] = ~acc[j];
+                fb[j] = T::fail_bits(acc[j]);
+            }
+        }
+        if (one_group) {
+#pragma unroll
+            for (int j = 0; j < NI; ++j) mine[j] |= fb[j];
+            continue;
+        }
+        const int g0 = __shfl_sync(0xffffffffu, wg, 0);
+        // a warp covers at most two word-set groups when m >= 32; anything else goes the slow way
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const uint32_t r0 = __reduce_or_sync(0xffffffffu, (valid && wg == g0) ? fb[j] : 0u);
+            const uint32_t r1 = __reduce_or_sync(0xffffffffu, (valid && wg == g0 + 1) ? fb[j] : 0u);
+            if (lane_id == 0) {
+                if (r0) atomicOr(&ctrl->fail[g0 * NI + j], r0);
+                if (r1) atomicOr(&ctrl->fail[(g0 + 1) * NI + j], r1);
+            }
+            if (valid && wg > g0 + 1 && fb[j]) atomicOr(&ctrl->fail[wg * NI + j], fb[j]);
+        }
+    }
+    if (one_group && tid - lane_id < items) {
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const uint32_t r = __reduce_or_sync(0xffffffffu, mine[j]);
+            if (lane_id == 0 && r) atomicOr(&ctrl->fail[j], r);
+        }
+    }
+}
+
+// forward pass of the fused schedule for the thread's check items (`fresh_only`: just the word-set groups a
+// new frame moved into); `vote`: the XOR words are a syndrome somebody waits for
+template <class T, int DC, bool REG, int NI, int IPT>
+__device__ __forceinline__ void forward_pass(const KParams &p, Ctrl *ctrl, const uint32_t *edge, const uint8_t *cdeg_s,
+                                             CheckState<DC, NI> (&st)[IPT], int items, int m, int E, int W,
+                                             bool fresh_only, bool vote)
+{
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
+    uint32_t mine[NI];
+#pragma unroll
+    for (int j = 0; j < NI; ++j) mine[j] = 0u;
+#pragma unroll
+    for (int q = 0; q < IPT; ++q) {
+        const int i = tid + q * nthreads;
+        if (i < items) {
+            const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
+            if (fresh_only) {
+                uint32_t touched = 0;
+#pragma unroll
+                for (int j = 0; j < NI; ++j) touched |= ctrl->fresh[wg * NI + j];
+                if (!touched) continue;
+            }
+            const uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
+            if (REG) {
+                check_forward<T, DC, DC, NI>(e0, m, E, st[q]);
+            } else {
+                const int d = cdeg_s[c];
+                LDPC_DEGREE_SWITCH(d, DC, (check_forward<T, D, DC, NI>(e0, m, E, st[q])))
+            }
+            if (vote) {
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    const uint32_t fb = T::fail_bits(st[q].acc[j]);
+                    if (W == NI) mine[j] |= fb;
+                    else if (fb) atomicOr(&ctrl->fail[wg * NI + j], fb);
+                }
+            }
+        }
+    }
+    if (vote && W == NI) {
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const uint32_t r = __reduce_or_sync(0xffffffffu, mine[j]);
+            if (lane_id == 0 && r) atomicOr(&ctrl->fail[j], r);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -842,12 +1120,15 @@ __device__ __forceinline__ uint32_t bookkeeping(const KParams &p, Ctrl *ctrl, in
 //        > 0: fused schedule -- every thread keeps the forward results of its <= IPT check items in registers,
 //        the syndrome falls out of the forward pass, the stop decision and the refill happen between the
 //        forward and the backward pass, and no word is read a third time.  Needs items <= IPT * threads.
+// A frame moves into a slot in the state the reference's initialisation leaves (every message = the channel
+// value), so one trip of the main loop is exactly one iteration of ArrayLDPC_Decoder.cpp:63-168 for every
+// resident frame: check phase, variable phase, syndrome, stop decision.
 // ------------------------------------------------------------------------------------------
 template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int IPT>
 __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
     // the named codes get their dimensions as compile-time constants: every k*m word offset of the check
     // phase then folds into the load/store immediate
     const int n = N ? N : p.n, m = M ? M : p.m, E = M ? DC * M : p.E, W = p.W;
@@ -866,7 +1147,10 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
 
     for (int i = tid; i < W * (E + n + m); i += nthreads) smem[i] = 0u;
     if (tid < MAX_W) { ctrl->fail[tid] = 0u; ctrl->fresh[tid] = 0u; ctrl->gflag[tid] = 0u; ctrl->failed[tid] = 0u; }
-    if (tid < MAX_SLOTS) { ctrl->fid[tid] = -1; ctrl->it[tid] = 0; }
+    if (tid < MAX_SLOTS) {
+        ctrl->fid[tid] = -1; ctrl->it[tid] = 0; ctrl->newfid[tid] = -1;
+        ctrl->next[tid] = (p.claim_ahead && tid < nslots) ? queue_frame(p, atomicAdd(p.queue, 1ull), frames) : -1;
+    }
     if (tid < 2) ctrl->fin[tid] = 0u;
     __syncthreads();
     unsigned int trip = 0;
@@ -880,72 +1164,22 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
 #define LDPC_MARK(k) do { } while (0)
 #endif
 
+    uint32_t fin = all_slots;  // slots to (re)fill
+    bool first = true;
     if (IPT > 0) {
         // ============================================================ fused schedule
         CheckState<DC, NI> st[IPT > 0 ? IPT : 1];
-        bool first = true;
+        const bool want_vote = p.precheck || p.max_iter == 0;
         for (;;) {
-            // ---- forward pass + syndrome of the state the last variable phase left
-            uint32_t mine[NI];
-#pragma unroll
-            for (int j = 0; j < NI; ++j) mine[j] = 0u;
-#pragma unroll
-            for (int q = 0; q < IPT; ++q) {
-                const int i = tid + q * nthreads;
-                if (i < items) {
-                    const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
-                    const uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
-                    if (REG) {
-                        check_forward<T, DC, DC, NI>(e0, m, E, st[q]);
-                    } else {
-                        const int d = cdeg_s[c];
-                        LDPC_DEGREE_SWITCH(d, DC, (check_forward<T, D, DC, NI>(e0, m, E, st[q])))
-                    }
-#pragma unroll
-                    for (int j = 0; j < NI; ++j) {
-                        const uint32_t fb = T::fail_bits(st[q].acc[j]);
-                        if (W == NI) mine[j] |= fb;
-                        else if (fb) atomicOr(&ctrl->fail[wg * NI + j], fb);
-                    }
-                }
-            }
-            if (W == NI) {
-#pragma unroll
-                for (int j = 0; j < NI; ++j) {
-                    const uint32_t r = __reduce_or_sync(0xffffffffu, mine[j]);
-                    if (lane_id == 0 && r) atomicOr(&ctrl->fail[j], r);
-                }
-            }
-            __syncthreads();
-            LDPC_MARK(3);
-
-            // ---- stop decision, results, refill
-            uint32_t fin = bookkeeping<T>(p, ctrl, W, trip);
-            if (first) fin = all_slots;
-            if (fin) {
-                const int active = finish_and_refill<T, DC, REG, REGV>(p, ctrl, edge, llr, cdeg_s, vdeg_s, fin, first, n, m, E, W, frames);
-                if (active == 0) break;
+            // ---- results of the frames that stopped, refill; fresh frames may stop at once (pre-check), so loop
+            while (fin) {
+                const int active = finish_and_refill<T, DC, DV, REG, REGV>(p, ctrl, edge, llr, cdeg_s, vdeg_s, fin, first, n, m, E, W, frames);
+                if (active == 0) goto done;
                 first = false;
-                // a refilled lane starts from zeros: redo the forward pass of the checks in the word sets it touched
-#pragma unroll
-                for (int q = 0; q < IPT; ++q) {
-                    const int i = tid + q * nthreads;
-                    if (i < items) {
-                        const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
-                        uint32_t touched = 0;
-#pragma unroll
-                        for (int j = 0; j < NI; ++j) touched |= ctrl->fresh[wg * NI + j];
-                        if (touched) {
-                            const uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
-                            if (REG) {
-                                check_forward<T, DC, DC, NI>(e0, m, E, st[q]);
-                            } else {
-                                const int d = cdeg_s[c];
-                                LDPC_DEGREE_SWITCH(d, DC, (check_forward<T, D, DC, NI>(e0, m, E, st[q])))
-                            }
-                        }
-                    }
-                }
+                // forward pass of the checks in the word sets that received a new frame (their other lane repeats itself)
+                forward_pass<T, DC, REG, NI, (IPT > 0 ? IPT : 1)>(p, ctrl, edge, cdeg_s, st, items, m, E, W, true, want_vote);
+                __syncthreads();
+                fin = bookkeeping_fresh<T>(p, ctrl, W, trip);
             }
             LDPC_MARK(0);
 
@@ -972,138 +1206,73 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
             else variable_phase<T, DV, false, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
             __syncthreads();
             LDPC_MARK(2);
+
+            // ---- forward pass of the next iteration; its XOR words are the syndrome of this one
+            forward_pass<T, DC, REG, NI, (IPT > 0 ? IPT : 1)>(p, ctrl, edge, cdeg_s, st, items, m, E, W, false, true);
+            __syncthreads();
+            LDPC_MARK(3);
+            fin = bookkeeping<T>(p, ctrl, W, trip);
+            LDPC_MARK(4);
         }
     } else {
-    // ================================================================ schedule with a separate syndrome pass
-    uint32_t fin = all_slots;  // slots to (re)fill
-    bool first = true;
-    for (;;) {
-        // ---------------------------------------------------------------- finish + refill
-        if (fin) {
-            const int active = finish_and_refill<T, DC, REG, REGV>(p, ctrl, edge, llr, cdeg_s, vdeg_s, fin, first, n, m, E, W, frames);
-            if (active == 0) break;
-            first = false;
-        }
-        LDPC_MARK(0);
-        // ---------------------------------------------------------------- check phase
-        for (int i = tid; i < items; i += nthreads) {
-            const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
-            uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
-            const uint32_t *nacc0 = cxor + (size_t)(wg * NI) * m + c;
-            if (REG) {
-                check_nodes<T, DC, NI>(e0, m, E, nacc0, NI);
-            } else {
-                const int d = cdeg_s[c];
-                bool done = false;
-                if (DC <= 16) {
-                    switch (d) {
+        // ============================================================ schedule with a separate syndrome pass
+        for (;;) {
+            // ---- finish + refill; fresh frames may stop at once (pre-check), so loop
+            while (fin) {
+                const int active = finish_and_refill<T, DC, DV, REG, REGV>(p, ctrl, edge, llr, cdeg_s, vdeg_s, fin, first, n, m, E, W, frames);
+                if (active == 0) goto done;
+                first = false;
+                // the new frames' words changed: refresh the per-check XOR words (and collect their syndrome)
+                syndrome_pass<T, DC, REG, NI>(p, ctrl, edge, cxor, cdeg_s, items, m, E, W);
+                __syncthreads();
+                fin = bookkeeping_fresh<T>(p, ctrl, W, trip);
+            }
+            LDPC_MARK(0);
+
+            // ---- check phase
+            for (int i = tid; i < items; i += nthreads) {
+                const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
+                uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
+                const uint32_t *nacc0 = cxor + (size_t)(wg * NI) * m + c;
+                if (REG) {
+                    check_nodes<T, DC, NI>(e0, m, E, nacc0, NI);
+                } else {
+                    const int d = cdeg_s[c];
+                    bool done = false;
+                    if (DC <= 16) {
+                        switch (d) {
 #define LDPC_CCASE(D) case D: if (D <= DC) { check_nodes<T, (D <= DC ? D : 2), NI>(e0, m, E, nacc0, NI); done = true; } break;
-                        LDPC_CCASE(2) LDPC_CCASE(3) LDPC_CCASE(4) LDPC_CCASE(5) LDPC_CCASE(6) LDPC_CCASE(7) LDPC_CCASE(8)
-                        LDPC_CCASE(9) LDPC_CCASE(10) LDPC_CCASE(11) LDPC_CCASE(12) LDPC_CCASE(13) LDPC_CCASE(14)
-                        LDPC_CCASE(15) LDPC_CCASE(16)
+                            LDPC_CCASE(2) LDPC_CCASE(3) LDPC_CCASE(4) LDPC_CCASE(5) LDPC_CCASE(6) LDPC_CCASE(7) LDPC_CCASE(8)
+                            LDPC_CCASE(9) LDPC_CCASE(10) LDPC_CCASE(11) LDPC_CCASE(12) LDPC_CCASE(13) LDPC_CCASE(14)
+                            LDPC_CCASE(15) LDPC_CCASE(16)
 #undef LDPC_CCASE
-                    default: break;
-                    }
-                }
-                if (!done)
-                    for (int j = 0; j < NI; ++j) check_node_any<T, DC>(e0 + (size_t)j * E, m, d, nacc0[j * m]);
-            }
-        }
-        __syncthreads();
-        LDPC_MARK(1);
-
-        // ---------------------------------------------------------------- variable phase
-        if (p.post) variable_phase<T, DV, true, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
-        else variable_phase<T, DV, false, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
-        __syncthreads();
-        LDPC_MARK(2);
-
-        // ---------------------------------------------------------------- syndrome pass
-        {
-            // When the CTA holds a single word-set group (W == NI) every item votes for the same NI word sets: the
-            // thread ORs its items' verdicts in registers and the warp reduces once, after the loop.
-            const bool one_group = (W == NI);
-            uint32_t mine[NI];
-#pragma unroll
-            for (int j = 0; j < NI; ++j) mine[j] = 0u;
-            for (int i0 = tid - lane_id; i0 < items; i0 += nthreads) {
-                const int i = i0 + lane_id;
-                const bool valid = i < items;
-                int wg = 0;
-                uint32_t fb[NI];
-#pragma unroll
-                for (int j = 0; j < NI; ++j) fb[j] = 0u;
-                if (valid) {
-                    wg = (int)__umulhi((uint32_t)i, p.inv_m);
-                    const int c = i - wg * m;
-                    const uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
-                    uint32_t acc[NI];
-                    if (REG) {
-                        check_xors<DC, NI>(e0, m, E, NI, acc);
-                    } else {
-                        const int d = cdeg_s[c];
-                        bool done = false;
-                        if (DC <= 16) {
-                            switch (d) {
-#define LDPC_XCASE(D) case D: if (D <= DC) { check_xors<(D <= DC ? D : 2), NI>(e0, m, E, NI, acc); done = true; } break;
-                                LDPC_XCASE(2) LDPC_XCASE(3) LDPC_XCASE(4) LDPC_XCASE(5) LDPC_XCASE(6) LDPC_XCASE(7) LDPC_XCASE(8)
-                                LDPC_XCASE(9) LDPC_XCASE(10) LDPC_XCASE(11) LDPC_XCASE(12) LDPC_XCASE(13) LDPC_XCASE(14)
-                                LDPC_XCASE(15) LDPC_XCASE(16)
-#undef LDPC_XCASE
-                            default: break;
-                            }
-                        }
-                        if (!done) {
-#pragma unroll
-                            for (int j = 0; j < NI; ++j) {
-                                uint32_t a = 0;
-#pragma unroll
-                                for (int k = 0; k < DC; ++k)
-                                    if (k < d) a ^= e0[(size_t)j * E + k * m];
-                                acc[j] = a;
-                            }
+                        default: break;
                         }
                     }
-#pragma unroll
-                    for (int j = 0; j < NI; ++j) {
-                        cxor[(size_t)(wg * NI + j) * m + c] = ~acc[j];
-                        fb[j] = T::fail_bits(acc[j]);
-                    }
-                }
-                if (one_group) {
-#pragma unroll
-                    for (int j = 0; j < NI; ++j) mine[j] |= fb[j];
-                    continue;
-                }
-                const int g0 = __shfl_sync(0xffffffffu, wg, 0);
-                // a warp covers at most two word-set groups when m >= 32; anything else goes the slow way
-#pragma unroll
-                for (int j = 0; j < NI; ++j) {
-                    const uint32_t r0 = __reduce_or_sync(0xffffffffu, (valid && wg == g0) ? fb[j] : 0u);
-                    const uint32_t r1 = __reduce_or_sync(0xffffffffu, (valid && wg == g0 + 1) ? fb[j] : 0u);
-                    if (lane_id == 0) {
-                        if (r0) atomicOr(&ctrl->fail[g0 * NI + j], r0);
-                        if (r1) atomicOr(&ctrl->fail[(g0 + 1) * NI + j], r1);
-                    }
-                    if (valid && wg > g0 + 1 && fb[j]) atomicOr(&ctrl->fail[wg * NI + j], fb[j]);
+                    if (!done)
+                        for (int j = 0; j < NI; ++j) check_node_any<T, DC>(e0 + (size_t)j * E, m, d, nacc0[j * m]);
                 }
             }
-            if (one_group && tid - lane_id < items) {
-#pragma unroll
-                for (int j = 0; j < NI; ++j) {
-                    const uint32_t r = __reduce_or_sync(0xffffffffu, mine[j]);
-                    if (lane_id == 0 && r) atomicOr(&ctrl->fail[j], r);
-                }
-            }
-        }
-        __syncthreads();
-        LDPC_MARK(3);
+            __syncthreads();
+            LDPC_MARK(1);
 
-        // ---------------------------------------------------------------- bookkeeping
-        fin = bookkeeping<T>(p, ctrl, W, trip);
-        LDPC_MARK(4);
+            // ---- variable phase
+            if (p.post) variable_phase<T, DV, true, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
+            else variable_phase<T, DV, false, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
+            __syncthreads();
+            LDPC_MARK(2);
+
+            // ---- syndrome pass
+            syndrome_pass<T, DC, REG, NI>(p, ctrl, edge, cxor, cdeg_s, items, m, E, W);
+            __syncthreads();
+            LDPC_MARK(3);
+
+            // ---- stop decision
+            fin = bookkeeping<T>(p, ctrl, W, trip);
+            LDPC_MARK(4);
+        }
     }
-    }
+done:;
 #ifdef LDPC_PHASE_TIMING
     if (tid == 0 && blockIdx.x == 0)
         printf("phase cycles (CTA 0): refill %lld check %lld variable %lld syndrome %lld bookkeeping %lld\n", t_phase[0],
