@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libldpc_b200.so")
+# LDPC_B200_LIB: load another build of the same library (e.g. the -DLDPC_PHASE_TIMING one of scripts/phase_timing.sh)
+LIB_PATH = os.environ.get("LDPC_B200_LIB") or os.path.join(HERE, "libldpc_b200.so")
 
 FMT_AUTO, FMT_A, FMT_C = 0, 1, 3
 OK, ERR_IO, ERR_FORMAT, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5, -6, -7

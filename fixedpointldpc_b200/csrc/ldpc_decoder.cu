@@ -33,14 +33,12 @@ struct KernelChoice {
     int ni = 1;
     int ctas_per_sm = 1;
     bool cdeg_in_smem = false, vdeg_in_smem = false;
-    int ipt = 0;  // > 0: fused schedule, at most ipt check items per thread
 };
 
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int IPT> static KernelChoice make_choice()
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N> static KernelChoice make_choice()
 {
     KernelChoice k;
-    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, IPT>;
-    k.ipt = IPT;
+    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N>;
     k.max_threads = MAXT;
     k.ni = NI;
     k.ctas_per_sm = NCTA;
@@ -64,20 +62,18 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
     // Launch shapes below were chosen by measurement on B200 (profiles/r01/launch_shape_sweep.txt): for the long
     // checks more, smaller CTAs with one chain per thread beat two interleaved chains per thread (fewer registers,
     // half the unrolled code, four independent phase streams per SM); the short 802.11 checks prefer NI = 2.
-    // fused schedule (IPT > 0) where every check item fits one thread without spilling: +4 % on the long-check
-    // array codes; the 802.11 code (two items x two word sets per thread at 64 registers) is faster unfused
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 5 && c.m == 235 && c.n == 2209)          // array p47 r5
-        return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209, 1>();
-    if (regular && vregular && c.dc_max == 47 && c.dv_max == 24 && c.m == 1128 && c.n == 2209)
-        return make_choice<T, 47, true, 24, 1, 576, 1, 1128, 2209, 2>();   // array p47 r24 (two checks per thread)
+        return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209>();
+    if (regular && vregular && c.dc_max == 47 && c.dv_max == 24 && c.m == 1128 && c.n == 2209)        // array p47 r24
+        return make_choice<T, 47, true, 24, 1, 576, 1, 1128, 2209>();
     if (regular && vregular && c.dc_max == 28 && c.dv_max == 4 && c.m == 316 && c.n == 2212)          // cut79
-        return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212, 1>();
+        return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212>();
     if (c.dc_max == 8 && c.dv_max <= 12 && c.m == 972 && c.n == 1944)                                // 802.11n 1944 r1/2
-        return make_choice<T, 8, false, 12, 2, 512, 2, 972, 1944, 0>();
+        return make_choice<T, 8, false, 12, 2, 512, 2, 972, 1944>();
     // any other code: run-time dimensions
-    if (regular && c.dc_max == 47 && c.dv_max <= 5) return make_choice<T, 47, true, 5, 1, 256, 4, 0, 0, 0>();
-    if (c.dc_max <= 8 && c.dv_max <= 12) return make_choice<T, 8, false, 12, 2, 512, 2, 0, 0, 0>();
-    if (c.dc_max <= 64 && c.dv_max <= 32) return make_choice<T, 64, false, 32, 1, 512, 1, 0, 0, 0>();
+    if (regular && c.dc_max == 47 && c.dv_max <= 5) return make_choice<T, 47, true, 5, 1, 256, 4, 0, 0>();
+    if (c.dc_max <= 8 && c.dv_max <= 12) return make_choice<T, 8, false, 12, 2, 512, 2, 0, 0>();
+    if (c.dc_max <= 64 && c.dv_max <= 32) return make_choice<T, 64, false, 32, 1, 512, 1, 0, 0>();
     return KernelChoice();
 }
 
@@ -129,7 +125,7 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
     const ldpc_code &c = d.code;
     if (!k.fn) { set_error("check degree > 64 or variable degree > 32: no kernel instantiation"); return LDPC_ERR_UNSUPPORTED; }
     if ((long long)c.dc_max * c.m > 65535) { set_error("dc_max*m exceeds the 16-bit edge address space"); return LDPC_ERR_UNSUPPORTED; }
-    const int per_w = (c.dc_max * c.m + c.n + c.m) * 4;  // messages + channel values + per-check XOR
+    const int per_w = (c.dc_max * c.m + c.n) * 4;  // messages + channel values
     // co-resident CTAs share the SM's shared memory (228 KB minus 1 KB reserved per CTA)
     const int sm_total = d.max_smem + 1024;
     const int tables = (k.cdeg_in_smem ? ((c.m + 15) & ~15) : 0) + (k.vdeg_in_smem ? ((c.n + 15) & ~15) : 0);
@@ -159,11 +155,6 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
         if (e >= best_e - 0.03) best_t = t;  // largest CTA within 3% of the best lane efficiency
     }
     if (want_threads > 0) best_t = std::min(k.max_threads, std::max(32, (want_threads / 32) * 32));
-    if (k.ipt > 0) {  // fused schedule: every check item must have a thread that keeps its forward results
-        const int need = (((items + k.ipt - 1) / k.ipt) + 31) / 32 * 32;
-        if (need > k.max_threads) { set_error("fused schedule: too many check items per CTA"); return LDPC_ERR_UNSUPPORTED; }
-        best_t = std::max(best_t, need);
-    }
     out.kernel = k; out.W = W; out.threads = best_t;
     out.smem = W * per_w + (int)sizeof(Ctrl) + tables;
     cudaError_t e = cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, out.smem);
@@ -232,8 +223,6 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     const int lanes = which == 0 ? 2 : 1;
     const long long slots = (long long)pl.W * lanes;
     int grid = (int)std::min<long long>((long long)d.sm_count * pl.kernel.ctas_per_sm, (frames + slots - 1) / slots);
-    p.has_deg0 = 0;
-    for (int v = 0; v < c.n; ++v) p.has_deg0 |= (c.vdeg[v] == 0);
     // Slots take their next frame from the queue one frame early (hides the atomic and lets the channel values be
     // prefetched into L2); with a short queue that would starve the CTAs that start last.  The length of an
     // indirect queue (re-decode list) is only known on the device.
@@ -253,6 +242,9 @@ static int decode_device(ldpc_decoder &d, const void *llr, int llr_bits, long lo
     if (frames > 0x7fffffffLL) { set_error("more than 2^31-1 frames in one call"); return LDPC_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(d.device));
     d.stats.frames += (uint64_t)frames;
+    // parity-mode message dump: the variable phase writes the real edges of every iteration; the unused slots of
+    // short rows read as zero like the reference's untouched EdgeRAM words
+    if (v2c) CUDA_TRY(cudaMemsetAsync(v2c, 0, (size_t)frames * d.code.dc_max * d.code.m * sizeof(int), st));
     if (d.cfg.precision == 32)
         return launch(d, d.plan32, 1, llr, llr_bits, frames, iters, bits, post, v2c, nullptr, nullptr, st, mc);
     int rc = launch(d, d.plan16, 0, llr, llr_bits, frames, iters, bits, post, v2c, nullptr, nullptr, st, mc);

@@ -8,15 +8,15 @@
 // early termination never idles the other slots.
 //
 // Per trip of the main loop (== one flooding iteration of ArrayLDPC_Decoder.cpp:63-168 for
-// every resident frame):
+// every resident frame, rotated so that the syndrome needs no pass of its own):
 //   variable phase  (ArrayLDPC_Decoder.cpp:121-156)  thread per variable, gather over the
-//                   static edge-address table; also writes the hard decision of the
-//                   posterior into a spare bit of every outgoing message
-//   syndrome pass   (ArrayLDPC_Decoder.cpp:296-333)  thread per check XORs those spare bits
-//   bookkeeping     early termination / max_iter / pre-check (:164-167, :443-450), output,
-//                   slot refill
-//   check phase     (ArrayLDPC_Decoder.cpp:66-118)   thread per check, forward chain kept in
-//                   registers, backward chain + combine fused with the write-back
+//                   static edge-address table; the hard decision of the posterior goes
+//                   into a spare bit of every outgoing message and of the channel word
+//   check phase     (ArrayLDPC_Decoder.cpp:66-118, 296-333)  thread per check: forward chain
+//                   in registers (XOR-ing the hard decisions on the way: the syndrome),
+//                   backward chain + combine fused with the write-back
+//   stop decision   early termination / max_iter / pre-check (:164-167, :443-450); stopping
+//                   frames leave (results from the bit array) and the next ones move in
 //
 // Message words in shared memory
 //   v2c (variable -> check): sign | hd | magnitude   (Scalar32: bit31 | bit30 | 30 bits,
@@ -43,7 +43,6 @@ struct KParams {
     int max_iter;  // MAX_ITER; 0 = hard decision + syndrome only (iters output: 0 pass, 1 fail)
     uint32_t inv_m;  // floor(2^32 / m) + 1: i / m == umulhi(i, inv_m) for i < 2^16
     int precheck;  // decode_fixpoint's hardDecision pre-check
-    int has_deg0;  // some variable takes part in no check (its hard decision comes from the channel word)
     int claim_ahead;  // every slot takes its next frame index one frame early (long queues only)
     // io
     const void *llr;  // [frames][n] int32 or int16
@@ -156,6 +155,10 @@ struct Scalar32 {
         return (w & SIGN) ? -mag : mag;
     }
     __device__ static __forceinline__ uint32_t hd_bit(uint32_t w, int) { return (w >> 30) & 1u; }
+    // A channel word also carries the hard decision of the variable's last posterior in bit 30, which is a copy of
+    // the sign bit as long as |LLR| < 2^30: llr_restore() gives the channel value back, llr_with_hd() stores the bit.
+    __device__ static __forceinline__ uint32_t llr_restore(uint32_t x) { return (x & ~HD) | ((x >> 1) & HD); }
+    __device__ static __forceinline__ uint32_t llr_with_hd(uint32_t x, uint32_t hd) { return (x & ~HD) | hd; }
     // lane content of a channel word / of a fresh frame's message word: v2c(0) = channel value
     // (ArrayLDPC_Decoder.cpp:45-61), carrying that value's hard decision
     __device__ static __forceinline__ uint32_t llr_lane(int val, bool &bad)
@@ -251,6 +254,10 @@ struct Packed16 {
         return (h & 0x8000u) ? -mag : mag;
     }
     __device__ static __forceinline__ uint32_t hd_bit(uint32_t w, int lane) { return (w >> (lane ? 30 : 14)) & 1u; }
+    // channel lanes stay below LLR_LIMIT < 2^13 in magnitude, so bit 14 of a lane is a copy of its sign bit and
+    // can carry the hard decision of the variable's last posterior (see Scalar32)
+    __device__ static __forceinline__ uint32_t llr_restore(uint32_t x) { return (x & ~HD) | ((x >> 1) & HD); }
+    __device__ static __forceinline__ uint32_t llr_with_hd(uint32_t x, uint32_t hd) { return (x & ~HD) | hd; }
     // Channel values are admitted below LLR_LIMIT, slightly under 2^13, so that the unclamped posterior of a
     // degree <= 2 variable cannot wrap its lane: LLR_LIMIT-1 + 2*C2V_MAX + C2V_MAX < 2^15, where
     // C2V_MAX = 2^13-1 + 20 bounds every check output (each sxor adds at most 10 to the smaller magnitude).
@@ -362,87 +369,104 @@ __device__ __forceinline__ uint32_t cw_bit(const KParams &p, long long f, int v)
 }
 
 // ------------------------------------------------------------------------------------------
-// control block in shared memory (after the message and channel words)
+// control block in shared memory (after the message words, channel words and hard-decision bits)
 // ------------------------------------------------------------------------------------------
 constexpr int MAX_W = 16;         // word sets per CTA
 constexpr bool PREFETCH_VEDGE = true;   // software-prefetch the next variable's edge addresses (costs registers)
 constexpr int MAX_SLOTS = 2 * MAX_W;
 
 struct Ctrl {
-    uint32_t fail[MAX_W];   // per word set: lanes with at least one unsatisfied check
-    uint32_t fresh[MAX_W];  // per word set: lanes refilled since the last bookkeeping step (iteration count 0)
+    uint32_t fail[MAX_W];   // per word set: lanes with at least one unsatisfied check (votes of the check phase)
+    uint32_t fresh[MAX_W];  // per word set: lanes that moved in since the last stop decision (iteration count stays 0)
     uint32_t gflag[MAX_W];  // per word set: lanes that left the guard range (Packed16)
-    uint32_t failed[MAX_W]; // copy of `fail` from the last bookkeeping step, read by the finish code
+    uint32_t failed[MAX_W]; // copy of `fail` from the last stop decision, read by the finish code
     int fid[MAX_SLOTS];     // frame index decoded in the slot, -1 = idle
     int next[MAX_SLOTS];    // frame the slot decodes after this one (taken from the queue one frame early), -1 = none
     int newfid[MAX_SLOTS];  // frame moving into the slot during a refill
     int it[MAX_SLOTS];      // iterations completed by that frame
     uint32_t lehmer[MAX_SLOTS];  // Lehmer state before the slot's frame (MC mode 2)
     unsigned int errs[MAX_SLOTS];  // info-bit errors of the frames being finished (MC mode)
-    uint32_t fin[2];        // slots that stop, written in the bookkeeping step; indexed by loop-trip parity
+    uint32_t fin[2];        // slots that stop, written at the stop decision; indexed by loop-trip parity
 };
 
 // ------------------------------------------------------------------------------------------
-// check phase: NI independent check nodes of exact degree D per thread, interleaved instruction
-// by instruction so every thread carries NI dependency chains (the chains are serial by
-// construction -- sxor is not associative -- and one chain per thread leaves the ALU pipe idle).
-// The NI nodes are the same check c in NI consecutive word sets: e[i] = e0 + i*wstride.
+// check phase (ArrayLDPC_Decoder.cpp:66-118 + the syndrome of :296-333): NI independent check nodes of exact
+// degree D per thread, interleaved instruction by instruction so every thread carries NI dependency chains
+// (the chains are serial by construction -- sxor is not associative -- and one chain per thread leaves the
+// ALU pipe idle).  The NI nodes are the same check c in NI consecutive word sets: e[i] = e0 + i*wstride.
+//
+// The forward chain F[k] = g(F[k-1], m[k]) stays in registers; on the way it XORs the incoming words: bit 30/14
+// of the XOR is the parity of the senders' hard decisions -- this check's syndrome bit for the state the last
+// variable phase left (returned in fb) -- and bit 31/15 the parity of the signs, so bit 31/15 of
+// (~xor ^ word_k) is the inverted sign of the outgoing message of slot k.  The backward chain and the combine
+// c2v[k] = g(F[k-1], B[k+1]) walk back down, re-reading each word once and overwriting it in place.
 // ------------------------------------------------------------------------------------------
 template <class T, int D, int NI>
-__device__ __forceinline__ void check_nodes(uint32_t *e0, int m, int wstride, const uint32_t *nacc0, int nvalid)
+__device__ __forceinline__ void check_nodes(uint32_t *e0, int m, int wstride, uint32_t (&fb)[NI])
 {
-    uint32_t fwd[NI][D - 1], w0[NI], bwd[NI], nacc[NI];
+    uint32_t fwd[NI][D - 1], w0[NI], nacc[NI], bwd[NI];
     uint32_t *e[NI];
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-        // word sets past the last one alias the first (loads stay in bounds, stores are predicated off)
-        e[i] = e0 + (i < nvalid ? i * wstride : 0);
-        nacc[i] = nacc0[i < nvalid ? i * m : 0];
+        e[i] = e0 + i * wstride;
         w0[i] = e[i][0];
+        nacc[i] = w0[i];
         fwd[i][0] = w0[i] & T::MAG;
     }
 #pragma unroll
     for (int k = 1; k < D - 1; ++k)
 #pragma unroll
-        for (int i = 0; i < NI; ++i) fwd[i][k] = T::g(fwd[i][k - 1], e[i][k * m] & T::MAG);
-    // nacc = ~XOR of all incoming words (from the syndrome pass); bit 31/15 of (nacc ^ word_k) is
-    // the inverted sign of the outgoing message of slot k.
+        for (int i = 0; i < NI; ++i) {
+            const uint32_t w = e[i][k * m];
+            nacc[i] ^= w;
+            fwd[i][k] = T::g(fwd[i][k - 1], w & T::MAG);
+        }
+    // The backward pass reads every word a second time (volatile: otherwise the compiler keeps the D words of the
+    // forward pass alive and, out of registers, parks them in local memory -- which is L2 here).
 #pragma unroll
     for (int k = D - 1; k >= 1; --k)
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
-            const uint32_t w = e[i][k * m];
+            const uint32_t w = k == D - 1 ? e[i][k * m] : *reinterpret_cast<volatile uint32_t *>(&e[i][k * m]);
             const uint32_t mag = w & T::MAG;
             uint32_t o;
             if (k == D - 1) {
+                nacc[i] ^= w;
+                fb[i] = T::fail_bits(nacc[i]);
+                nacc[i] = ~nacc[i];
                 o = fwd[i][D - 2];  // c2v[d-1] = Forward[d-2]
                 bwd[i] = mag;
             } else {
                 o = T::g(fwd[i][k - 1], bwd[i]);  // c2v[k] = sxor(Forward[k-1], Backward[k+1])
                 bwd[i] = T::g(bwd[i], mag);       // Backward[k]
             }
-            if (i < nvalid) e[i][k * m] = T::neg_c2v(o, nacc[i] ^ w);
+            e[i][k * m] = T::neg_c2v(o, nacc[i] ^ w);
         }
 #pragma unroll
-    for (int i = 0; i < NI; ++i)
-        if (i < nvalid) e[i][0] = T::neg_c2v(bwd[i], nacc[i] ^ w0[i]);  // c2v[0] = Backward[1]
+    for (int i = 0; i < NI; ++i) e[i][0] = T::neg_c2v(bwd[i], nacc[i] ^ w0[i]);  // c2v[0] = Backward[1]
 }
 
-// one check node of run-time degree d <= DC (predicated; only for degrees without an exact body)
+// one check node of run-time degree 2 <= d <= DC (predicated; only for degrees without an exact body)
 template <class T, int DC>
-__device__ __forceinline__ void check_node_any(uint32_t *e, int m, int d, const uint32_t nacc)
+__device__ __forceinline__ uint32_t check_node_any(uint32_t *e, int m, int d)
 {
     uint32_t fwd[DC - 1];
     const uint32_t w0 = e[0];
+    uint32_t nacc = w0;
     fwd[0] = w0 & T::MAG;
     uint32_t last = fwd[0];  // ends as Forward[d-2] without a runtime-indexed read of fwd[]
 #pragma unroll
     for (int k = 1; k < DC - 1; ++k) {
         if (k < d - 1) {
-            fwd[k] = T::g(fwd[k - 1], e[k * m] & T::MAG);
+            const uint32_t w = e[k * m];
+            nacc ^= w;
+            fwd[k] = T::g(fwd[k - 1], w & T::MAG);
             last = fwd[k];
         }
     }
+    nacc ^= e[(d - 1) * m];
+    const uint32_t fb = T::fail_bits(nacc);
+    nacc = ~nacc;
     uint32_t bwd = 0;
 #pragma unroll
     for (int k = DC - 1; k >= 1; --k) {
@@ -461,36 +485,98 @@ __device__ __forceinline__ void check_node_any(uint32_t *e, int m, int d, const 
         }
     }
     e[0] = T::neg_c2v(bwd, nacc ^ w0);
+    return fb;
 }
 
-// syndrome pass for the same NI word sets: XOR of the D incoming words of the check
-template <int D, int NI>
-__device__ __forceinline__ void check_xors(const uint32_t *e0, int m, int wstride, int nvalid, uint32_t (&acc)[NI])
+// thread per (word-set group, check); the syndrome bits are OR-ed into ctrl->fail, one shared atomic per warp
+template <class T, int DC, bool REG, int NI>
+__device__ __forceinline__ void check_phase(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint8_t *cdeg_s,
+                                            int items, int m, int E, int W)
 {
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
+    // When the CTA holds a single word-set group (W == NI) every item votes for the same NI word sets: the
+    // thread ORs its items' verdicts in registers and the warp reduces once, after the loop.
+    const bool one_group = (W == NI);
+    uint32_t mine[NI];
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-        const uint32_t *e = e0 + (i < nvalid ? i * wstride : 0);
-        uint32_t a = e[0];
+    for (int j = 0; j < NI; ++j) mine[j] = 0u;
+    for (int i0 = tid - lane_id; i0 < items; i0 += nthreads) {
+        const int i = i0 + lane_id;
+        const bool valid = i < items;
+        int wg = 0;
+        uint32_t fb[NI];
 #pragma unroll
-        for (int k = 1; k + 1 < D; k += 2) a = xor3(a, e[k * m], e[(k + 1) * m]);
-        if ((D - 1) % 2) a ^= e[(D - 1) * m];
-        acc[i] = a;
+        for (int j = 0; j < NI; ++j) fb[j] = 0u;
+        if (valid) {
+            wg = (int)__umulhi((uint32_t)i, p.inv_m);
+            const int c = i - wg * m;
+            uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
+            if (REG) {
+                check_nodes<T, DC, NI>(e0, m, E, fb);
+            } else {
+                const int d = cdeg_s[c];
+                bool done = false;
+                if (DC <= 16) {
+                    // exact-degree bodies: no per-edge predicates or branches inside
+                    switch (d) {
+#define LDPC_CCASE(D) case D: if (D <= DC) { check_nodes<T, (D <= DC ? D : 2), NI>(e0, m, E, fb); done = true; } break;
+                        LDPC_CCASE(2) LDPC_CCASE(3) LDPC_CCASE(4) LDPC_CCASE(5) LDPC_CCASE(6) LDPC_CCASE(7) LDPC_CCASE(8)
+                        LDPC_CCASE(9) LDPC_CCASE(10) LDPC_CCASE(11) LDPC_CCASE(12) LDPC_CCASE(13) LDPC_CCASE(14)
+                        LDPC_CCASE(15) LDPC_CCASE(16)
+#undef LDPC_CCASE
+                    default: break;
+                    }
+                }
+                if (!done)  // the loader rejects checks of degree < 2
+                    for (int j = 0; j < NI; ++j) fb[j] = check_node_any<T, DC>(e0 + (size_t)j * E, m, d);
+            }
+        }
+        if (one_group) {
+#pragma unroll
+            for (int j = 0; j < NI; ++j) mine[j] |= fb[j];
+            continue;
+        }
+        const int g0 = __shfl_sync(0xffffffffu, wg, 0);
+        // a warp covers at most two word-set groups when m >= 32; anything else goes the slow way
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const uint32_t r0 = __reduce_or_sync(0xffffffffu, (valid && wg == g0) ? fb[j] : 0u);
+            const uint32_t r1 = __reduce_or_sync(0xffffffffu, (valid && wg == g0 + 1) ? fb[j] : 0u);
+            if (lane_id == 0) {
+                if (r0) atomicOr(&ctrl->fail[g0 * NI + j], r0);
+                if (r1) atomicOr(&ctrl->fail[(g0 + 1) * NI + j], r1);
+            }
+            if (valid && wg > g0 + 1 && fb[j]) atomicOr(&ctrl->fail[wg * NI + j], fb[j]);
+        }
+    }
+    if (one_group && tid - lane_id < items) {
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const uint32_t r = __reduce_or_sync(0xffffffffu, mine[j]);
+            if (lane_id == 0 && r) atomicOr(&ctrl->fail[j], r);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // variable phase for one variable node of exact degree D (ArrayLDPC_Decoder.cpp:121-156:
 // post = LLR + sum c2v, v2c_j = post - c2v_j), NW word sets at a time for instruction-level
-// parallelism.  POST: also store the posteriors (parity mode).
+// parallelism.  The hard decision of the posterior rides in a spare bit of every outgoing message (the check
+// phase XORs them into the syndrome) and is also kept in a spare bit of the variable's channel word, which
+// is what a stopping frame's result is read from after the check phase has overwritten the messages.
+// PARITY: also store the posteriors and the messages of every iteration (parity-mode outputs; the last
+// iteration's survive).
 // ------------------------------------------------------------------------------------------
-template <class T, int D, int NW, bool POST>
+
+template <class T, int D, int NW, bool PARITY>
 __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, char *base, uint32_t stride,
-                                               const uint32_t (&off)[D], const uint32_t *llr, int v, int w, int n)
+                                               const uint32_t *off, uint32_t *llr, int v, int w, int n)
 {
-    uint32_t x[NW][D], pw[NW], hd[NW], guard[NW];
+    uint32_t x[NW][D > 0 ? D : 1], pw[NW], hd[NW], guard[NW], lx[NW];
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
-        typename T::Acc acc = T::acc_init(llr[(w + i) * n + v]);
+        lx[i] = T::llr_restore(llr[(w + i) * n + v]);
+        typename T::Acc acc = T::acc_init(lx[i]);
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             x[i][j] = *reinterpret_cast<uint32_t *>(base + i * stride + off[j]);
@@ -505,9 +591,11 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, cha
         for (int i = 0; i < NW; ++i) {
             const uint32_t a = T::v2c_signmag(pw[i], x[i][j]);
             *reinterpret_cast<uint32_t *>(base + i * stride + off[j]) = a | hd[i];
+            x[i][j] = a;
             if (j + 1 < D) {
                 const uint32_t b = T::v2c_signmag(pw[i], x[i][j + 1]);
                 *reinterpret_cast<uint32_t *>(base + i * stride + off[j + 1]) = b | hd[i];
+                x[i][j + 1] = b;
                 guard[i] = or3(guard[i], a, b);
             } else {
                 guard[i] |= a;
@@ -516,45 +604,53 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, cha
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
         if (T::guard_hit(guard[i])) atomicOr(&ctrl->gflag[w + i], T::guard_lanes(guard[i]));
-        if (POST) {
+        llr[(w + i) * n + v] = T::llr_with_hd(lx[i], hd[i]);
+        if (PARITY) {
 #pragma unroll
             for (int lane = 0; lane < T::LANES; ++lane) {
                 const int f = ctrl->fid[(w + i) * T::LANES + lane];
-                if (f >= 0) p.post[(size_t)f * n + v] = T::lane_value(pw[i], lane);
+                if (f < 0) continue;
+                if (p.post) p.post[(size_t)f * n + v] = T::lane_value(pw[i], lane);
+                if (p.v2c) {
+                    int *out = p.v2c + (size_t)f * p.dc_max * p.m;  // EdgeRAM order: [slot][check]
+#pragma unroll
+                    for (int j = 0; j < D; ++j) out[off[j] >> 2] = T::v2c_value(x[i][j], lane);
+                }
             }
         }
     }
 }
 
-template <class T, int D, bool POST>
-__device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr,
-                                              int v, int W, int n, int E, const uint32_t (&off)[D])
+template <class T, int D, bool PARITY>
+__device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
+                                              int v, int W, int n, int E, const uint32_t *off)
 {
     char *base = reinterpret_cast<char *>(edge);
     const uint32_t stride = (uint32_t)E * 4u;
     int w = 0;
-    for (; w + 1 < W; w += 2, base += 2 * stride) variable_words<T, D, 2, POST>(p, ctrl, base, stride, off, llr, v, w, n);
-    if (w < W) variable_words<T, D, 1, POST>(p, ctrl, base, stride, off, llr, v, w, n);
+    for (; w + 1 < W; w += 2, base += 2 * stride) variable_words<T, D, 2, PARITY>(p, ctrl, base, stride, off, llr, v, w, n);
+    if (w < W) variable_words<T, D, 1, PARITY>(p, ctrl, base, stride, off, llr, v, w, n);
 }
 
-template <class T, int D, bool POST>
-__device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr,
+template <class T, int D, bool PARITY>
+__device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
                                               int v, int W, int n, int E)
 {
-    uint32_t off[D];  // byte offsets of the D edge words inside a word set
+    uint32_t off[D > 0 ? D : 1];  // byte offsets of the D edge words inside a word set
 #pragma unroll
     for (int j = 0; j < D; ++j) off[j] = (uint32_t)p.vedge[j * n + v] * 4u;
-    variable_node<T, D, POST>(p, ctrl, edge, llr, v, W, n, E, off);
+    variable_node<T, D, PARITY>(p, ctrl, edge, llr, v, W, n, E, off);
 }
 
 // any degree (slow path for degrees without an exact instantiation): two passes over the words
 template <class T>
-__device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr,
+__device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
                                                   int v, int W, int dv, int n, int E)
 {
     for (int w = 0; w < W; ++w) {
         uint32_t *ew = edge + (size_t)w * E;
-        typename T::Acc acc = T::acc_init(llr[(size_t)w * n + v]);
+        const uint32_t lx = T::llr_restore(llr[(size_t)w * n + v]);
+        typename T::Acc acc = T::acc_init(lx);
         for (int j = 0; j < dv; ++j) T::acc_sub(acc, ew[p.vedge[(size_t)j * n + v]]);
         uint32_t hd, guard = 0;
         const uint32_t pw = T::template post_word<64>(acc, hd);
@@ -565,19 +661,24 @@ __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, 
             *q = a | hd;
         }
         if (T::guard_hit(guard)) atomicOr(&ctrl->gflag[w], T::guard_lanes(guard));
-        if (p.post) {
-            for (int lane = 0; lane < T::LANES; ++lane) {
-                const int f = ctrl->fid[w * T::LANES + lane];
-                if (f >= 0) p.post[(size_t)f * n + v] = T::lane_value(pw, lane);
-            }
+        llr[(size_t)w * n + v] = T::llr_with_hd(lx, hd);
+        for (int lane = 0; lane < T::LANES; ++lane) {
+            const int f = ctrl->fid[w * T::LANES + lane];
+            if (f < 0) continue;
+            if (p.post) p.post[(size_t)f * n + v] = T::lane_value(pw, lane);
+            if (p.v2c)
+                for (int j = 0; j < dv; ++j) {
+                    const uint32_t a = p.vedge[(size_t)j * n + v];
+                    p.v2c[(size_t)f * p.dc_max * p.m + a] = T::v2c_value(ew[a], lane);
+                }
         }
     }
 }
 
 // REGV: every variable has degree DV -- the edge addresses of the thread's next variable are fetched while the
 // current one is processed (the table lives in global memory / L2)
-template <class T, int DV, bool POST, bool REGV>
-__device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint32_t *llr, int W,
+template <class T, int DV, bool PARITY, bool REGV>
+__device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr, int W,
                                                int n, int E, const uint8_t *vdeg)
 {
     if (REGV) {
@@ -592,7 +693,7 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
             const int vn = v + blockDim.x;
 #pragma unroll
             for (int j = 0; j < DV; ++j) next[j] = vn < n ? (uint32_t)p.vedge[j * n + vn] * 4u : 0u;
-            variable_node<T, DV, POST>(p, ctrl, edge, llr, v, W, n, E, off);
+            variable_node<T, DV, PARITY>(p, ctrl, edge, llr, v, W, n, E, off);
         }
     } else
     for (int v = threadIdx.x; v < n; v += blockDim.x) {
@@ -601,170 +702,35 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
         if (DV <= 12) {
             // exact-degree bodies: no per-edge predicates or branches inside
             switch (dv) {
-#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), POST>(p, ctrl, edge, llr, v, W, n, E); done = true; } break;
-                LDPC_VCASE(1) LDPC_VCASE(2) LDPC_VCASE(3) LDPC_VCASE(4) LDPC_VCASE(5) LDPC_VCASE(6)
+#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), PARITY>(p, ctrl, edge, llr, v, W, n, E); done = true; } break;
+                LDPC_VCASE(0) LDPC_VCASE(1) LDPC_VCASE(2) LDPC_VCASE(3) LDPC_VCASE(4) LDPC_VCASE(5) LDPC_VCASE(6)
                 LDPC_VCASE(7) LDPC_VCASE(8) LDPC_VCASE(9) LDPC_VCASE(10) LDPC_VCASE(11) LDPC_VCASE(12)
 #undef LDPC_VCASE
             default: break;
             }
         } else if (dv == DV) {
-            variable_node<T, DV, POST>(p, ctrl, edge, llr, v, W, n, E);
+            variable_node<T, DV, PARITY>(p, ctrl, edge, llr, v, W, n, E);
             done = true;
         }
         if (!done) variable_node_any<T>(p, ctrl, edge, llr, v, W, dv, n, E);
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// split check node for the fused schedule: the forward pass also yields the XOR of the incoming
-// words (syndrome + sign parity), the backward pass runs after the stop decision
-// ------------------------------------------------------------------------------------------
-template <int DC, int NI> struct CheckState {
-    uint32_t fwd[NI][DC - 1];
-    uint32_t w0[NI];
-    uint32_t acc[NI];
-};
-
-template <class T, int D, int DC, int NI>
-__device__ __forceinline__ void check_forward(const uint32_t *e0, int m, int wstride, CheckState<DC, NI> &st)
+// parity-mode variant (posteriors and messages written through every iteration): kept out of line so that its
+// register needs do not shape the allocation of the throughput path
+template <class T, int DV, bool REGV>
+__device__ __noinline__ void variable_phase_parity(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr, int W,
+                                                   int n, int E, const uint8_t *vdeg)
 {
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-        st.w0[i] = e0[i * wstride];
-        st.acc[i] = st.w0[i];
-        st.fwd[i][0] = st.w0[i] & T::MAG;
-    }
-#pragma unroll
-    for (int k = 1; k < D; ++k)
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            const uint32_t w = e0[i * wstride + k * m];
-            st.acc[i] ^= w;
-            if (k < D - 1) st.fwd[i][k] = T::g(st.fwd[i][k - 1], w & T::MAG);
-        }
+    variable_phase<T, DV, true, REGV>(p, ctrl, edge, llr, W, n, E, vdeg);
 }
 
-template <class T, int D, int DC, int NI>
-__device__ __forceinline__ void check_backward(uint32_t *e0, int m, int wstride, const CheckState<DC, NI> &st)
-{
-    uint32_t bwd[NI];
-#pragma unroll
-    for (int k = D - 1; k >= 1; --k)
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            uint32_t *e = e0 + i * wstride;
-            const uint32_t w = e[k * m];
-            const uint32_t mag = w & T::MAG;
-            uint32_t o;
-            if (k == D - 1) {
-                o = st.fwd[i][D - 2];
-                bwd[i] = mag;
-            } else {
-                o = T::g(st.fwd[i][k - 1], bwd[i]);
-                bwd[i] = T::g(bwd[i], mag);
-            }
-            e[k * m] = T::neg_c2v(o, ~st.acc[i] ^ w);
-        }
-#pragma unroll
-    for (int i = 0; i < NI; ++i) e0[i * wstride] = T::neg_c2v(bwd[i], ~st.acc[i] ^ st.w0[i]);
-}
-
-#define LDPC_DEGREE_SWITCH(d, DCMAX, CALL)                                                             \
-    switch (d) {                                                                                       \
-        case 2: { constexpr int D = 2 <= DCMAX ? 2 : 2; CALL; } break;                                   \
-        case 3: { constexpr int D = 3 <= DCMAX ? 3 : 2; CALL; } break;                                   \
-        case 4: { constexpr int D = 4 <= DCMAX ? 4 : 2; CALL; } break;                                   \
-        case 5: { constexpr int D = 5 <= DCMAX ? 5 : 2; CALL; } break;                                   \
-        case 6: { constexpr int D = 6 <= DCMAX ? 6 : 2; CALL; } break;                                   \
-        case 7: { constexpr int D = 7 <= DCMAX ? 7 : 2; CALL; } break;                                   \
-        case 8: { constexpr int D = 8 <= DCMAX ? 8 : 2; CALL; } break;                                   \
-        default: break;                                                                                \
-    }
-
 // ------------------------------------------------------------------------------------------
-// refill
+// results of stopping frames, refill
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2(const void *ptr)
 {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-}
-
-// One pass over the variables for the slots in `fin`, thread per variable:
-//   emit  the hard decisions of the frame that leaves the slot (ballot over 32 consecutive variables): packed
-//         bits and / or the error count of Monte-Carlo mode
-//   fill  the frame that moves in: its channel word and the message words of its edges, which start as
-//         v2c(0) = channel value (the reference's initialisation, ArrayLDPC_Decoder.cpp:45-61).  A lane is a
-//         16-bit half of its word (Packed16), so these are plain stores.
-// `from_smem`: the channel values were generated into the channel words already (Monte-Carlo mode); otherwise
-// they are read from global memory, UNR loads in flight per thread.  A thread reads the old hard decision of a
-// variable before it overwrites that variable's words, and nobody else touches them: no barrier in between.
-template <class T, int DV, bool REGV>
-__device__ __forceinline__ void fill_pass(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr, const uint8_t *vdeg_s,
-                                          uint32_t fin, bool emit, bool fill, bool from_smem, int n, int E)
-{
-    constexpr int UNR = 4;
-    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
-    uint32_t bad_slots = 0;
-    for (uint32_t left = fin; left; left &= left - 1u) {
-        const int s = __ffs(left) - 1;
-        const int w = s / T::LANES, lane = s % T::LANES;
-        const int fo = emit ? ctrl->fid[s] : -1, fn = ctrl->newfid[s];
-        uint32_t *ew = edge + (size_t)w * E, *lw = llr + (size_t)w * n;
-        const int16_t *g16 = reinterpret_cast<const int16_t *>(p.llr) + (size_t)(fn >= 0 ? fn : 0) * n;
-        const int *g32 = reinterpret_cast<const int *>(p.llr) + (size_t)(fn >= 0 ? fn : 0) * n;
-        for (int base = 0; base < n; base += UNR * nthreads) {
-            int val[UNR];
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int v = base + u * nthreads + tid;
-                val[u] = 0;
-                if (fill && v < n) {
-                    if (from_smem) val[u] = T::lane_value(lw[v], lane);
-                    else if (fn >= 0) val[u] = p.llr_bits == 16 ? (int)g16[v] : g32[v];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                if (base + u * nthreads < n) {  // uniform
-                    const int v = base + u * nthreads + tid;
-                    const int dv = v < n ? (REGV ? DV : (int)vdeg_s[v]) : 0;
-                    const uint32_t a0 = dv ? (uint32_t)p.vedge[v] : 0u;
-                    if (fo >= 0) {
-                        uint32_t b = 0;
-                        if (v < n) b = dv ? T::hd_bit(ew[a0], lane) : (uint32_t)(T::lane_value(lw[v], lane) <= 0);
-                        const uint32_t word = __ballot_sync(0xffffffffu, b);
-                        if (lane_id == 0 && v < n) {
-                            if (p.bits) p.bits[(size_t)fo * p.nw32 + (v >> 5)] = word;
-                            if (p.mc_mode != 0) {
-                                const uint32_t sent = p.mc_cw ? p.mc_cw[(size_t)fo * p.mc_cw_stride + (v >> 5)] : 0u;
-                                const uint32_t mask = p.mc_info ? p.mc_info[v >> 5] : 0xffffffffu;
-                                const unsigned int e = __popc((word ^ sent) & mask);
-                                if (e) atomicAdd(&ctrl->errs[s], e);
-                            }
-                        }
-                    }
-                    if (fill && v < n) {
-                        if (!from_smem) {
-                            bool bad;
-                            T::store_lane(&lw[v], lane, T::llr_lane(val[u], bad));
-                            if (bad) bad_slots |= 1u << s;
-                        }
-                        const uint32_t iw = T::init_lane(val[u]);
-                        if (REGV) {
-                            T::store_lane(&ew[a0], lane, iw);
-#pragma unroll
-                            for (int j = 1; j < DV; ++j) T::store_lane(&ew[p.vedge[j * n + v]], lane, iw);
-                        } else {
-#pragma unroll 4
-                            for (int j = 0; j < dv; ++j) T::store_lane(&ew[p.vedge[j * n + v]], lane, iw);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    for (int s = 0; bad_slots; ++s, bad_slots >>= 1)
-        if (bad_slots & 1u) atomicOr(&ctrl->gflag[s / T::LANES], 1u << (s % T::LANES));
 }
 
 // frame index behind queue position q (-1 past the end)
@@ -773,12 +739,30 @@ __device__ __forceinline__ int queue_frame(const KParams &p, unsigned long long 
     return q < (unsigned long long)frames ? (p.index ? p.index[q] : (int)q) : -1;
 }
 
-// Results of the slots in `fin` (unless `first`), then the next frames move in.  Returns the number of active
-// slots.  Called by every thread of the CTA (contains barriers).
-template <class T, int DC, int DV, bool REG, bool REGV>
+// hard decisions of 32 consecutive variables of the frame `fo` that leaves slot s: packed bits and / or the
+// error count of Monte-Carlo mode (calculateBER, ArrayLDPC_Decoder.cpp:707-722, on packed words)
+__device__ __forceinline__ void emit_word(const KParams &p, Ctrl *ctrl, int s, int fo, int v, int n, uint32_t bit)
+{
+    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+    if ((threadIdx.x & 31) == 0 && v < n) {
+        if (p.bits) p.bits[(size_t)fo * p.nw32 + (v >> 5)] = word;
+        if (p.mc_mode != 0) {
+            const uint32_t sent = p.mc_cw ? p.mc_cw[(size_t)fo * p.mc_cw_stride + (v >> 5)] : 0u;
+            const uint32_t mask = p.mc_info ? p.mc_info[v >> 5] : 0xffffffffu;
+            const unsigned int e = __popc((word ^ sent) & mask);
+            if (e) atomicAdd(&ctrl->errs[s], e);
+        }
+    }
+}
+
+// Results of the slots in `fin` (unless `first`), then the next frames move in: the lane's messages are cleared
+// and its channel values loaded or generated.  Zero messages make the next variable phase produce
+// post = LLR, v2c = LLR -- the reference's initialisation (ArrayLDPC_Decoder.cpp:45-61) -- for the new lane while
+// it runs an ordinary iteration for the lane's neighbour.  Returns the number of active slots.  Called by every
+// thread of the CTA (contains barriers).
+template <class T>
 __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
-                                                 const uint8_t *cdeg_s, const uint8_t *vdeg_s, uint32_t fin, bool first,
-                                                 int n, int m, int E, int W, long long frames)
+                                                 uint32_t fin, bool first, int n, int E, int W, long long frames)
 {
     const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
     const int nslots = W * T::LANES;
@@ -805,85 +789,94 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
         atomicAnd(&ctrl->gflag[w], ~(1u << lane));
     }
     __syncthreads();
-    if (!first && (p.post || p.v2c)) {  // parity mode: state of the stopping frames
+    if (p.mc_mode != 0 && emit) {
+        // Monte-Carlo mode generates the channel values with another thread-to-variable mapping, so the decoded
+        // bits (kept in the channel words) are collected first
         for (uint32_t left = fin; left; left &= left - 1u) {
             const int s = __ffs(left) - 1;
-            const int w = s / T::LANES, lane = s % T::LANES;
-            const int f = ctrl->fid[s];
-            if (p.post && ctrl->it[s] == 0)  // stopped before its first variable phase: posterior == channel value
-                for (int v = tid; v < n; v += nthreads) p.post[(size_t)f * n + v] = T::lane_value(llr[(size_t)w * n + v], lane);
-            if (p.v2c) {
-                const uint32_t *ew = edge + (size_t)w * E;
-                int *out = p.v2c + (size_t)f * p.dc_max * m;
-                for (int i = tid; i < p.dc_max * m; i += nthreads) {
-                    const int k = i / m, c = i - k * m;
-                    out[i] = k < (REG ? DC : (int)cdeg_s[c]) ? T::v2c_value(ew[i], lane) : 0;
+            const int fo = ctrl->fid[s];
+            const uint32_t *lw = llr + (size_t)(s / T::LANES) * n;
+            if (fo >= 0)
+                for (int base = 0; base < n; base += nthreads) {
+                    const int v = base + tid;
+                    emit_word(p, ctrl, s, fo, v, n, v < n ? T::hd_bit(lw[v], s % T::LANES) : 0u);
                 }
-            }
         }
         __syncthreads();
     }
-    if (p.mc_mode != 0) {
-        // Monte-Carlo mode: the channel values are generated into the channel words first
-        bool emitted = false;
-        if (emit && p.has_deg0) {  // a variable without edges keeps its hard decision in the channel word itself
-            fill_pass<T, DV, REGV>(p, ctrl, edge, llr, vdeg_s, fin, true, false, true, n, E);
-            __syncthreads();
-            emitted = true;
-        }
-        uint32_t bad_slots = 0;
-        if (p.mc_mode == 1) {
-            for (int q = tid; 4 * q < n; q += nthreads) {
-                for (uint32_t left = fin; left; left &= left - 1u) {
-                    const int s = __ffs(left) - 1;
-                    const int w = s / T::LANES, lane = s % T::LANES;
-                    const int f = ctrl->newfid[s];
-                    float z[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (f >= 0) philox_normals(p, p.mc_first + (unsigned long long)f, (uint32_t)q, z);
+    uint32_t bad_slots = 0;
+    for (uint32_t left = fin; left; left &= left - 1u) {
+        const int s = __ffs(left) - 1;
+        const int w = s / T::LANES, lane = s % T::LANES;
+        const int fo = emit ? ctrl->fid[s] : -1, fn = ctrl->newfid[s];
+        uint32_t *ew = edge + (size_t)w * E, *lw = llr + (size_t)w * n;
+        if (p.mc_mode == 0) {
+            // decoded bits of the frame that leaves (the hard decisions its last variable phase left in the channel
+            // words), then the channel values of the frame that moves in: same thread, same word, no barrier
+            constexpr int UNR = 4;  // loads in flight per thread
+            const int16_t *g16 = reinterpret_cast<const int16_t *>(p.llr) + (size_t)(fn >= 0 ? fn : 0) * n;
+            const int *g32 = reinterpret_cast<const int *>(p.llr) + (size_t)(fn >= 0 ? fn : 0) * n;
+            for (int base = 0; base < n; base += UNR * nthreads) {
+                int val[UNR];
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const int v = 4 * q + h;
+                for (int u = 0; u < UNR; ++u) {
+                    const int v = base + u * nthreads + tid;
+                    val[u] = 0;
+                    if (v < n && fn >= 0) val[u] = p.llr_bits == 16 ? (int)g16[v] : g32[v];
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    if (base + u * nthreads < n) {  // uniform
+                        const int v = base + u * nthreads + tid;
+                        if (fo >= 0) emit_word(p, ctrl, s, fo, v, n, v < n ? T::hd_bit(lw[v], lane) : 0u);
                         if (v < n) {
                             bool bad;
-                            const int val = f >= 0 ? quantise_llr(p, (double)z[h], cw_bit(p, f, v)) : 0;
-                            T::store_lane(&llr[(size_t)w * n + v], lane, T::llr_lane(val, bad));
+                            T::store_lane(&lw[v], lane, T::llr_lane(val[u], bad));
                             if (bad) bad_slots |= 1u << s;
                         }
                     }
                 }
             }
+        } else if (p.mc_mode == 1) {
+            for (int q = tid; 4 * q < n; q += nthreads) {
+                float z[4] = {0.f, 0.f, 0.f, 0.f};
+                if (fn >= 0) philox_normals(p, p.mc_first + (unsigned long long)fn, (uint32_t)q, z);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const int v = 4 * q + h;
+                    if (v < n) {
+                        bool bad;
+                        const int val = fn >= 0 ? quantise_llr(p, (double)z[h], cw_bit(p, fn, v)) : 0;
+                        T::store_lane(&lw[v], lane, T::llr_lane(val, bad));
+                        if (bad) bad_slots |= 1u << s;
+                    }
+                }
+            }
         } else {
             for (int v = tid; v < n; v += nthreads) {
-                const uint32_t pw = p.mc_pow[v];
-                for (uint32_t left = fin; left; left &= left - 1u) {
-                    const int s = __ffs(left) - 1;
-                    const int w = s / T::LANES, lane = s % T::LANES;
-                    const int f = ctrl->newfid[s];
-                    bool bad;
-                    const int val = f >= 0 ? quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], pw)), cw_bit(p, f, v)) : 0;
-                    T::store_lane(&llr[(size_t)w * n + v], lane, T::llr_lane(val, bad));
-                    if (bad) bad_slots |= 1u << s;
-                }
+                bool bad;
+                const int val = fn >= 0 ? quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], p.mc_pow[v])), cw_bit(p, fn, v)) : 0;
+                T::store_lane(&lw[v], lane, T::llr_lane(val, bad));
+                if (bad) bad_slots |= 1u << s;
             }
         }
-        for (int s = 0; bad_slots; ++s, bad_slots >>= 1)
-            if (bad_slots & 1u) atomicOr(&ctrl->gflag[s / T::LANES], 1u << (s % T::LANES));
+        // its messages start from zero
+        if (!first)
+            for (int i = tid; i < E; i += nthreads) T::store_lane(&ew[i], lane, 0u);
+    }
+    for (int s = 0; bad_slots; ++s, bad_slots >>= 1)
+        if (bad_slots & 1u) atomicOr(&ctrl->gflag[s / T::LANES], 1u << (s % T::LANES));
+    if (p.mc_mode != 0 && p.mc_pin_count > 0) {  // shortening: known positions pinned (PerfTest.cpp:410-414)
         __syncthreads();
-        if (p.mc_pin_count > 0) {  // shortening: known positions pinned (PerfTest.cpp:410-414)
-            for (int i = tid; i < p.mc_pin_count; i += nthreads) {
-                const int v = p.mc_pin[i];
-                for (uint32_t left = fin; left; left &= left - 1u) {
-                    const int s = __ffs(left) - 1;
-                    if (ctrl->newfid[s] < 0) continue;
-                    bool bad;
-                    T::store_lane(&llr[(size_t)(s / T::LANES) * n + v], s % T::LANES, T::llr_lane(p.mc_pin_value, bad));
-                }
+        for (int i = tid; i < p.mc_pin_count; i += nthreads) {
+            const int v = p.mc_pin[i];
+            for (uint32_t left = fin; left; left &= left - 1u) {
+                const int s = __ffs(left) - 1;
+                if (ctrl->newfid[s] < 0) continue;
+                bool bad;
+                T::store_lane(&llr[(size_t)(s / T::LANES) * n + v], s % T::LANES, T::llr_lane(p.mc_pin_value, bad));
             }
-            __syncthreads();
         }
-        fill_pass<T, DV, REGV>(p, ctrl, edge, llr, vdeg_s, fin, emit && !emitted, true, true, n, E);
-    } else {
-        fill_pass<T, DV, REGV>(p, ctrl, edge, llr, vdeg_s, fin, emit, true, false, n, E);
     }
     __syncthreads();
     int ahead = -1;
@@ -923,9 +916,13 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
     return active;
 }
 
-// stop / continue decision of every slot after an iteration and its syndrome; returns the mask of stopping slots
+// Stop / continue decision of every slot, taken after the check phase (its votes are the syndrome of the state the
+// variable phase before it left): early termination after every iteration (ArrayLDPC_Decoder.cpp:164-167),
+// MAX_ITER (:63), decode_fixpoint's pre-check on the channel hard decisions (:443-450, iteration count 0), the
+// hard-decision-only mode (max_iter == 0) and lanes that left the packed range.  A frame that just moved in has
+// only had its initialisation, so its iteration count stays 0.  Returns the mask of stopping slots.
 template <class T>
-__device__ __forceinline__ uint32_t bookkeeping(const KParams &p, Ctrl *ctrl, int W, unsigned int &trip)
+__device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, int W, unsigned int &trip)
 {
     const int tid = threadIdx.x, nslots = W * T::LANES;
     // one thread per slot decides; the stop mask travels through shared memory (double buffered by trip
@@ -933,35 +930,12 @@ __device__ __forceinline__ uint32_t bookkeeping(const KParams &p, Ctrl *ctrl, in
     if (tid < nslots) {
         const int s = tid, w = s / T::LANES, lane = s % T::LANES;
         if (ctrl->fid[s] >= 0) {
-            const int it = ctrl->it[s] + 1;
+            const bool fresh = (ctrl->fresh[w] >> lane) & 1u;
+            const int it = ctrl->it[s] + (fresh ? 0 : 1);
             const bool pass = !((ctrl->fail[w] >> lane) & 1u);
             const bool over = (ctrl->gflag[w] >> lane) & 1u;
             ctrl->it[s] = it;
-            if (it >= p.max_iter || pass || over) atomicOr(&ctrl->fin[trip & 1], 1u << s);
-        }
-    }
-    __syncthreads();
-    const uint32_t fin = ctrl->fin[trip & 1];
-    if (tid < W) { ctrl->failed[tid] = ctrl->fail[tid]; ctrl->fail[tid] = 0u; }
-    if (tid == 0) ctrl->fin[(trip + 1) & 1] = 0u;
-    ++trip;
-    if (fin) __syncthreads();  // the finish code reads what the threads above just wrote
-    return fin;
-}
-
-// the same decision for frames that were just loaded (iteration count 0): decode_fixpoint's pre-check
-// (ArrayLDPC_Decoder.cpp:443-450), the hard-decision-only mode (max_iter == 0) and frames whose channel values
-// already left the packed range.  Clears the `fresh` marks.
-template <class T>
-__device__ __forceinline__ uint32_t bookkeeping_fresh(const KParams &p, Ctrl *ctrl, int W, unsigned int &trip)
-{
-    const int tid = threadIdx.x, nslots = W * T::LANES;
-    if (tid < nslots) {
-        const int s = tid, w = s / T::LANES, lane = s % T::LANES;
-        if (ctrl->fid[s] >= 0 && ((ctrl->fresh[w] >> lane) & 1u)) {
-            const bool pass = !((ctrl->fail[w] >> lane) & 1u);
-            const bool over = (ctrl->gflag[w] >> lane) & 1u;
-            if (p.max_iter == 0 || (pass && p.precheck) || over) atomicOr(&ctrl->fin[trip & 1], 1u << s);
+            if (it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over) atomicOr(&ctrl->fin[trip & 1], 1u << s);
         }
     }
     __syncthreads();
@@ -969,163 +943,31 @@ __device__ __forceinline__ uint32_t bookkeeping_fresh(const KParams &p, Ctrl *ct
     if (tid < W) { ctrl->failed[tid] = ctrl->fail[tid]; ctrl->fail[tid] = 0u; ctrl->fresh[tid] = 0u; }
     if (tid == 0) ctrl->fin[(trip + 1) & 1] = 0u;
     ++trip;
-    __syncthreads();
+    if (fin) __syncthreads();  // the finish code reads what the threads above just wrote
     return fin;
-}
-
-// ------------------------------------------------------------------------------------------
-// syndrome pass (ArrayLDPC_Decoder.cpp:296-333), thread per check and group of NI word sets: XOR of the check's
-// incoming words.  Bit 30/14 is the parity of the hard decisions (the syndrome), bit 31/15 the parity of the
-// signs; the inverted word is kept for the next check phase.  Votes into ctrl->fail.
-// ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG, int NI>
-__device__ __forceinline__ void syndrome_pass(const KParams &p, Ctrl *ctrl, const uint32_t *edge, uint32_t *cxor,
-                                              const uint8_t *cdeg_s, int items, int m, int E, int W)
-{
-    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
-    // When the CTA holds a single word-set group (W == NI) every item votes for the same NI word sets: the
-    // thread ORs its items' verdicts in registers and the warp reduces once, after the loop.
-    const bool one_group = (W == NI);
-    uint32_t mine[NI];
-#pragma unroll
-    for (int j = 0; j < NI; ++j) mine[j] = 0u;
-    for (int i0 = tid - lane_id; i0 < items; i0 += nthreads) {
-        const int i = i0 + lane_id;
-        const bool valid = i < items;
-        int wg = 0;
-        uint32_t fb[NI];
-#pragma unroll
-        for (int j = 0; j < NI; ++j) fb[j] = 0u;
-        if (valid) {
-            wg = (int)__umulhi((uint32_t)i, p.inv_m);
-            const int c = i - wg * m;
-            const uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
-            uint32_t acc[NI];
-            if (REG) {
-                check_xors<DC, NI>(e0, m, E, NI, acc);
-            } else {
-                const int d = cdeg_s[c];
-                bool done = false;
-                if (DC <= 16) {
-                    switch (d) {
-#define LDPC_XCASE(D) case D: if (D <= DC) { check_xors<(D <= DC ? D : 2), NI>(e0, m, E, NI, acc); done = true; } break;
-                        LDPC_XCASE(2) LDPC_XCASE(3) LDPC_XCASE(4) LDPC_XCASE(5) LDPC_XCASE(6) LDPC_XCASE(7) LDPC_XCASE(8)
-                        LDPC_XCASE(9) LDPC_XCASE(10) LDPC_XCASE(11) LDPC_XCASE(12) LDPC_XCASE(13) LDPC_XCASE(14)
-                        LDPC_XCASE(15) LDPC_XCASE(16)
-#undef LDPC_XCASE
-                    default: break;
-                    }
-                }
-                if (!done) {
-#pragma unroll
-                    for (int j = 0; j < NI; ++j) {
-                        uint32_t a = 0;
-#pragma unroll
-                        for (int k = 0; k < DC; ++k)
-                            if (k < d) a ^= e0[(size_t)j * E + k * m];
-                        acc[j] = a;
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < NI; ++j) {
-                cxor[(size_t)(wg * NI + j) * m + c] = ~acc[j];
-                fb[j] = T::fail_bits(acc[j]);
-            }
-        }
-        if (one_group) {
-#pragma unroll
-            for (int j = 0; j < NI; ++j) mine[j] |= fb[j];
-            continue;
-        }
-        const int g0 = __shfl_sync(0xffffffffu, wg, 0);
-        // a warp covers at most two word-set groups when m >= 32; anything else goes the slow way
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-            const uint32_t r0 = __reduce_or_sync(0xffffffffu, (valid && wg == g0) ? fb[j] : 0u);
-            const uint32_t r1 = __reduce_or_sync(0xffffffffu, (valid && wg == g0 + 1) ? fb[j] : 0u);
-            if (lane_id == 0) {
-                if (r0) atomicOr(&ctrl->fail[g0 * NI + j], r0);
-                if (r1) atomicOr(&ctrl->fail[(g0 + 1) * NI + j], r1);
-            }
-            if (valid && wg > g0 + 1 && fb[j]) atomicOr(&ctrl->fail[wg * NI + j], fb[j]);
-        }
-    }
-    if (one_group && tid - lane_id < items) {
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-            const uint32_t r = __reduce_or_sync(0xffffffffu, mine[j]);
-            if (lane_id == 0 && r) atomicOr(&ctrl->fail[j], r);
-        }
-    }
-}
-
-// forward pass of the fused schedule for the thread's check items (`fresh_only`: just the word-set groups a
-// new frame moved into); `vote`: the XOR words are a syndrome somebody waits for
-template <class T, int DC, bool REG, int NI, int IPT>
-__device__ __forceinline__ void forward_pass(const KParams &p, Ctrl *ctrl, const uint32_t *edge, const uint8_t *cdeg_s,
-                                             CheckState<DC, NI> (&st)[IPT], int items, int m, int E, int W,
-                                             bool fresh_only, bool vote)
-{
-    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
-    uint32_t mine[NI];
-#pragma unroll
-    for (int j = 0; j < NI; ++j) mine[j] = 0u;
-#pragma unroll
-    for (int q = 0; q < IPT; ++q) {
-        const int i = tid + q * nthreads;
-        if (i < items) {
-            const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
-            if (fresh_only) {
-                uint32_t touched = 0;
-#pragma unroll
-                for (int j = 0; j < NI; ++j) touched |= ctrl->fresh[wg * NI + j];
-                if (!touched) continue;
-            }
-            const uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
-            if (REG) {
-                check_forward<T, DC, DC, NI>(e0, m, E, st[q]);
-            } else {
-                const int d = cdeg_s[c];
-                LDPC_DEGREE_SWITCH(d, DC, (check_forward<T, D, DC, NI>(e0, m, E, st[q])))
-            }
-            if (vote) {
-#pragma unroll
-                for (int j = 0; j < NI; ++j) {
-                    const uint32_t fb = T::fail_bits(st[q].acc[j]);
-                    if (W == NI) mine[j] |= fb;
-                    else if (fb) atomicOr(&ctrl->fail[wg * NI + j], fb);
-                }
-            }
-        }
-    }
-    if (vote && W == NI) {
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-            const uint32_t r = __reduce_or_sync(0xffffffffu, mine[j]);
-            if (lane_id == 0 && r) atomicOr(&ctrl->fail[j], r);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------
 // the kernel
 //   DC   largest check degree, REG: every check has degree DC
 //   DV   largest variable degree with an exact body
-//   NI   word sets per thread in the check / syndrome phases (W is a multiple of NI)
+//   NI   word sets per thread in the check phase (W is a multiple of NI)
 //   M, N compile-time m and n of the named codes (0 = read them from the parameters)
 //   MAXT, NCTA  launch bounds: CTA size and co-resident CTAs per SM.  Co-resident CTAs drift out of phase, so
 //        one's latency-bound variable phase overlaps the other's ALU-bound check phase.
-//   IPT  0: separate syndrome pass (any number of check items per thread);
-//        > 0: fused schedule -- every thread keeps the forward results of its <= IPT check items in registers,
-//        the syndrome falls out of the forward pass, the stop decision and the refill happen between the
-//        forward and the backward pass, and no word is read a third time.  Needs items <= IPT * threads.
-// A frame moves into a slot in the state the reference's initialisation leaves (every message = the channel
-// value), so one trip of the main loop is exactly one iteration of ArrayLDPC_Decoder.cpp:63-168 for every
-// resident frame: check phase, variable phase, syndrome, stop decision.
+//
+// One trip of the main loop is one iteration of ArrayLDPC_Decoder.cpp:63-168 for every resident frame, rotated so
+// that the syndrome needs no pass of its own:
+//     variable phase i   (for a frame that just moved in: the initialisation, :45-61)
+//     check phase i+1    which first XORs the hard decisions it reads -> syndrome after iteration i
+//     stop decision      frames whose syndrome is zero (or that reached MAX_ITER) leave with the hard decisions
+//                        the variable phase kept in the channel words; the messages check phase i+1 wrote for
+//                        them are never used
+// so a frame that stops costs one check phase more than the reference executes, and a converged frame is
+// found by the same two barriers per trip that the phases need anyway.
 // ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int IPT>
-__global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N>
+__global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constant__ KParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -1133,9 +975,8 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
     // phase then folds into the load/store immediate
     const int n = N ? N : p.n, m = M ? M : p.m, E = M ? DC * M : p.E, W = p.W;
     uint32_t *edge = smem;                 // [W][E]
-    uint32_t *llr = edge + (size_t)W * E;  // [W][n]
-    uint32_t *cxor = llr + (size_t)W * n;  // [W][m] inverted XOR of every check's incoming words (IPT == 0)
-    Ctrl *ctrl = reinterpret_cast<Ctrl *>(cxor + (size_t)W * m);
+    uint32_t *llr = edge + (size_t)W * E;  // [W][n] channel values (+ the hard decision of the last posterior)
+    Ctrl *ctrl = reinterpret_cast<Ctrl *>(llr + (size_t)W * n);
     // degree tables next to the control block (irregular codes dispatch on them once per node and phase)
     constexpr bool REGV = PREFETCH_VEDGE && M != 0 && REG && DV <= 8;
     uint8_t *cdeg_s = reinterpret_cast<uint8_t *>(ctrl + 1);
@@ -1145,7 +986,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
     const int nslots = W * T::LANES;
     const long long frames = p.count ? (long long)*p.count : p.frames;
 
-    for (int i = tid; i < W * (E + n + m); i += nthreads) smem[i] = 0u;
+    for (int i = tid; i < W * (E + n); i += nthreads) smem[i] = 0u;
     if (tid < MAX_W) { ctrl->fail[tid] = 0u; ctrl->fresh[tid] = 0u; ctrl->gflag[tid] = 0u; ctrl->failed[tid] = 0u; }
     if (tid < MAX_SLOTS) {
         ctrl->fid[tid] = -1; ctrl->it[tid] = 0; ctrl->newfid[tid] = -1;
@@ -1155,128 +996,37 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const KParams p)
     __syncthreads();
     unsigned int trip = 0;
 
-    const uint32_t all_slots = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);
     const int items = (W / NI) * m;  // (word-set group, check)
 #ifdef LDPC_PHASE_TIMING
-    long long t_phase[5] = {0, 0, 0, 0, 0}, t_mark = clock64();
+    long long t_phase[4] = {0, 0, 0, 0}, t_mark = clock64();
 #define LDPC_MARK(k) do { long long t_now = clock64(); t_phase[k] += t_now - t_mark; t_mark = t_now; } while (0)
 #else
 #define LDPC_MARK(k) do { } while (0)
 #endif
 
-    uint32_t fin = all_slots;  // slots to (re)fill
+    uint32_t fin = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);  // slots to (re)fill
     bool first = true;
-    if (IPT > 0) {
-        // ============================================================ fused schedule
-        CheckState<DC, NI> st[IPT > 0 ? IPT : 1];
-        const bool want_vote = p.precheck || p.max_iter == 0;
-        for (;;) {
-            // ---- results of the frames that stopped, refill; fresh frames may stop at once (pre-check), so loop
-            while (fin) {
-                const int active = finish_and_refill<T, DC, DV, REG, REGV>(p, ctrl, edge, llr, cdeg_s, vdeg_s, fin, first, n, m, E, W, frames);
-                if (active == 0) goto done;
-                first = false;
-                // forward pass of the checks in the word sets that received a new frame (their other lane repeats itself)
-                forward_pass<T, DC, REG, NI, (IPT > 0 ? IPT : 1)>(p, ctrl, edge, cdeg_s, st, items, m, E, W, true, want_vote);
-                __syncthreads();
-                fin = bookkeeping_fresh<T>(p, ctrl, W, trip);
-            }
-            LDPC_MARK(0);
-
-            // ---- backward pass + write-back
-#pragma unroll
-            for (int q = 0; q < IPT; ++q) {
-                const int i = tid + q * nthreads;
-                if (i < items) {
-                    const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
-                    uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
-                    if (REG) {
-                        check_backward<T, DC, DC, NI>(e0, m, E, st[q]);
-                    } else {
-                        const int d = cdeg_s[c];
-                        LDPC_DEGREE_SWITCH(d, DC, (check_backward<T, D, DC, NI>(e0, m, E, st[q])))
-                    }
-                }
-            }
-            __syncthreads();
-            LDPC_MARK(1);
-
-            // ---- variable phase
-            if (p.post) variable_phase<T, DV, true, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
-            else variable_phase<T, DV, false, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
-            __syncthreads();
-            LDPC_MARK(2);
-
-            // ---- forward pass of the next iteration; its XOR words are the syndrome of this one
-            forward_pass<T, DC, REG, NI, (IPT > 0 ? IPT : 1)>(p, ctrl, edge, cdeg_s, st, items, m, E, W, false, true);
-            __syncthreads();
-            LDPC_MARK(3);
-            fin = bookkeeping<T>(p, ctrl, W, trip);
-            LDPC_MARK(4);
+    for (;;) {
+        if (fin) {
+            const int active = finish_and_refill<T>(p, ctrl, edge, llr, fin, first, n, E, W, frames);
+            if (active == 0) break;
+            first = false;
         }
-    } else {
-        // ============================================================ schedule with a separate syndrome pass
-        for (;;) {
-            // ---- finish + refill; fresh frames may stop at once (pre-check), so loop
-            while (fin) {
-                const int active = finish_and_refill<T, DC, DV, REG, REGV>(p, ctrl, edge, llr, cdeg_s, vdeg_s, fin, first, n, m, E, W, frames);
-                if (active == 0) goto done;
-                first = false;
-                // the new frames' words changed: refresh the per-check XOR words (and collect their syndrome)
-                syndrome_pass<T, DC, REG, NI>(p, ctrl, edge, cxor, cdeg_s, items, m, E, W);
-                __syncthreads();
-                fin = bookkeeping_fresh<T>(p, ctrl, W, trip);
-            }
-            LDPC_MARK(0);
-
-            // ---- check phase
-            for (int i = tid; i < items; i += nthreads) {
-                const int wg = (int)__umulhi((uint32_t)i, p.inv_m), c = i - wg * m;
-                uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
-                const uint32_t *nacc0 = cxor + (size_t)(wg * NI) * m + c;
-                if (REG) {
-                    check_nodes<T, DC, NI>(e0, m, E, nacc0, NI);
-                } else {
-                    const int d = cdeg_s[c];
-                    bool done = false;
-                    if (DC <= 16) {
-                        switch (d) {
-#define LDPC_CCASE(D) case D: if (D <= DC) { check_nodes<T, (D <= DC ? D : 2), NI>(e0, m, E, nacc0, NI); done = true; } break;
-                            LDPC_CCASE(2) LDPC_CCASE(3) LDPC_CCASE(4) LDPC_CCASE(5) LDPC_CCASE(6) LDPC_CCASE(7) LDPC_CCASE(8)
-                            LDPC_CCASE(9) LDPC_CCASE(10) LDPC_CCASE(11) LDPC_CCASE(12) LDPC_CCASE(13) LDPC_CCASE(14)
-                            LDPC_CCASE(15) LDPC_CCASE(16)
-#undef LDPC_CCASE
-                        default: break;
-                        }
-                    }
-                    if (!done)
-                        for (int j = 0; j < NI; ++j) check_node_any<T, DC>(e0 + (size_t)j * E, m, d, nacc0[j * m]);
-                }
-            }
-            __syncthreads();
-            LDPC_MARK(1);
-
-            // ---- variable phase
-            if (p.post) variable_phase<T, DV, true, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
-            else variable_phase<T, DV, false, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
-            __syncthreads();
-            LDPC_MARK(2);
-
-            // ---- syndrome pass
-            syndrome_pass<T, DC, REG, NI>(p, ctrl, edge, cxor, cdeg_s, items, m, E, W);
-            __syncthreads();
-            LDPC_MARK(3);
-
-            // ---- stop decision
-            fin = bookkeeping<T>(p, ctrl, W, trip);
-            LDPC_MARK(4);
-        }
+        LDPC_MARK(0);
+        if (p.post || p.v2c) variable_phase_parity<T, DV, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
+        else variable_phase<T, DV, false, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
+        __syncthreads();
+        LDPC_MARK(1);
+        check_phase<T, DC, REG, NI>(p, ctrl, edge, cdeg_s, items, m, E, W);
+        __syncthreads();
+        LDPC_MARK(2);
+        fin = stop_decision<T>(p, ctrl, W, trip);
+        LDPC_MARK(3);
     }
-done:;
 #ifdef LDPC_PHASE_TIMING
-    if (tid == 0 && blockIdx.x == 0)
-        printf("phase cycles (CTA 0): refill %lld check %lld variable %lld syndrome %lld bookkeeping %lld\n", t_phase[0],
-               t_phase[1], t_phase[2], t_phase[3], t_phase[4]);
+    if (tid == 0 && blockIdx.x == 0 && trip > 0)
+        printf("phase cycles (CTA 0): results+refill %lld variable %lld check %lld stop decision %lld | trips %u\n", t_phase[0],
+               t_phase[1], t_phase[2], t_phase[3], trip);
 #endif
 }
 
