@@ -376,17 +376,17 @@ constexpr bool PREFETCH_VEDGE = true;   // software-prefetch the next variable's
 constexpr int MAX_SLOTS = 2 * MAX_W;
 
 struct Ctrl {
-    uint32_t fail[MAX_W];   // per word set: lanes with at least one unsatisfied check (votes of the check phase)
-    uint32_t fresh[MAX_W];  // per word set: lanes that moved in since the last stop decision (iteration count stays 0)
-    uint32_t gflag[MAX_W];  // per word set: lanes that left the guard range (Packed16)
-    uint32_t failed[MAX_W]; // copy of `fail` from the last stop decision, read by the finish code
+    // Votes of one trip, read by that trip's stop decision.  Every thread takes the decision for itself, without a
+    // barrier, so these words rotate through three buffers (trip % 3): the buffer a trip writes was cleared two
+    // decisions ago and is next touched two barriers later.
+    uint32_t fail[3][MAX_W];   // per word set: lanes with at least one unsatisfied check (check phase)
+    uint32_t gflag[3][MAX_W];  // per word set: lanes that left the guard range (variable phase / load; Packed16)
     int fid[MAX_SLOTS];     // frame index decoded in the slot, -1 = idle
     int next[MAX_SLOTS];    // frame the slot decodes after this one (taken from the queue one frame early), -1 = none
     int newfid[MAX_SLOTS];  // frame moving into the slot during a refill
-    int it[MAX_SLOTS];      // iterations completed by that frame
+    unsigned int start[MAX_SLOTS];  // trip in which the slot's frame moved in: iterations completed = trip - start
     uint32_t lehmer[MAX_SLOTS];  // Lehmer state before the slot's frame (MC mode 2)
     unsigned int errs[MAX_SLOTS];  // info-bit errors of the frames being finished (MC mode)
-    uint32_t fin[2];        // slots that stop, written at the stop decision; indexed by loop-trip parity
 };
 
 // ------------------------------------------------------------------------------------------
@@ -488,9 +488,9 @@ __device__ __forceinline__ uint32_t check_node_any(uint32_t *e, int m, int d)
     return fb;
 }
 
-// thread per (word-set group, check); the syndrome bits are OR-ed into ctrl->fail, one shared atomic per warp
+// thread per (word-set group, check); the syndrome bits are OR-ed into fail[word set], one shared atomic per warp
 template <class T, int DC, bool REG, int NI>
-__device__ __forceinline__ void check_phase(const KParams &p, Ctrl *ctrl, uint32_t *edge, const uint8_t *cdeg_s,
+__device__ __forceinline__ void check_phase(const KParams &p, uint32_t *fail, uint32_t *edge, const uint8_t *cdeg_s,
                                             int items, int m, int E, int W)
 {
     const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
@@ -543,17 +543,17 @@ __device__ __forceinline__ void check_phase(const KParams &p, Ctrl *ctrl, uint32
             const uint32_t r0 = __reduce_or_sync(0xffffffffu, (valid && wg == g0) ? fb[j] : 0u);
             const uint32_t r1 = __reduce_or_sync(0xffffffffu, (valid && wg == g0 + 1) ? fb[j] : 0u);
             if (lane_id == 0) {
-                if (r0) atomicOr(&ctrl->fail[g0 * NI + j], r0);
-                if (r1) atomicOr(&ctrl->fail[(g0 + 1) * NI + j], r1);
+                if (r0) atomicOr(&fail[g0 * NI + j], r0);
+                if (r1) atomicOr(&fail[(g0 + 1) * NI + j], r1);
             }
-            if (valid && wg > g0 + 1 && fb[j]) atomicOr(&ctrl->fail[wg * NI + j], fb[j]);
+            if (valid && wg > g0 + 1 && fb[j]) atomicOr(&fail[wg * NI + j], fb[j]);
         }
     }
     if (one_group && tid - lane_id < items) {
 #pragma unroll
         for (int j = 0; j < NI; ++j) {
             const uint32_t r = __reduce_or_sync(0xffffffffu, mine[j]);
-            if (lane_id == 0 && r) atomicOr(&ctrl->fail[j], r);
+            if (lane_id == 0 && r) atomicOr(&fail[j], r);
         }
     }
 }
@@ -569,7 +569,7 @@ __device__ __forceinline__ void check_phase(const KParams &p, Ctrl *ctrl, uint32
 // ------------------------------------------------------------------------------------------
 
 template <class T, int D, int NW, bool PARITY>
-__device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, char *base, uint32_t stride,
+__device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uint32_t *gflag, char *base, uint32_t stride,
                                                const uint32_t *off, uint32_t *llr, int v, int w, int n)
 {
     uint32_t x[NW][D > 0 ? D : 1], pw[NW], hd[NW], guard[NW], lx[NW];
@@ -603,7 +603,7 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, cha
         }
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
-        if (T::guard_hit(guard[i])) atomicOr(&ctrl->gflag[w + i], T::guard_lanes(guard[i]));
+        if (T::guard_hit(guard[i])) atomicOr(&gflag[w + i], T::guard_lanes(guard[i]));
         llr[(w + i) * n + v] = T::llr_with_hd(lx[i], hd[i]);
         if (PARITY) {
 #pragma unroll
@@ -622,29 +622,29 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, cha
 }
 
 template <class T, int D, bool PARITY>
-__device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
+__device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
                                               int v, int W, int n, int E, const uint32_t *off)
 {
     char *base = reinterpret_cast<char *>(edge);
     const uint32_t stride = (uint32_t)E * 4u;
     int w = 0;
-    for (; w + 1 < W; w += 2, base += 2 * stride) variable_words<T, D, 2, PARITY>(p, ctrl, base, stride, off, llr, v, w, n);
-    if (w < W) variable_words<T, D, 1, PARITY>(p, ctrl, base, stride, off, llr, v, w, n);
+    for (; w + 1 < W; w += 2, base += 2 * stride) variable_words<T, D, 2, PARITY>(p, ctrl, gflag, base, stride, off, llr, v, w, n);
+    if (w < W) variable_words<T, D, 1, PARITY>(p, ctrl, gflag, base, stride, off, llr, v, w, n);
 }
 
 template <class T, int D, bool PARITY>
-__device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
+__device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
                                               int v, int W, int n, int E)
 {
     uint32_t off[D > 0 ? D : 1];  // byte offsets of the D edge words inside a word set
 #pragma unroll
     for (int j = 0; j < D; ++j) off[j] = (uint32_t)p.vedge[j * n + v] * 4u;
-    variable_node<T, D, PARITY>(p, ctrl, edge, llr, v, W, n, E, off);
+    variable_node<T, D, PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E, off);
 }
 
 // any degree (slow path for degrees without an exact instantiation): two passes over the words
 template <class T>
-__device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
+__device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
                                                   int v, int W, int dv, int n, int E)
 {
     for (int w = 0; w < W; ++w) {
@@ -660,7 +660,7 @@ __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, 
             guard |= a;
             *q = a | hd;
         }
-        if (T::guard_hit(guard)) atomicOr(&ctrl->gflag[w], T::guard_lanes(guard));
+        if (T::guard_hit(guard)) atomicOr(&gflag[w], T::guard_lanes(guard));
         llr[(size_t)w * n + v] = T::llr_with_hd(lx, hd);
         for (int lane = 0; lane < T::LANES; ++lane) {
             const int f = ctrl->fid[w * T::LANES + lane];
@@ -678,7 +678,7 @@ __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, 
 // REGV: every variable has degree DV -- the edge addresses of the thread's next variable are fetched while the
 // current one is processed (the table lives in global memory / L2)
 template <class T, int DV, bool PARITY, bool REGV>
-__device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr, int W,
+__device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
                                                int n, int E, const uint8_t *vdeg)
 {
     if (REGV) {
@@ -693,7 +693,7 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
             const int vn = v + blockDim.x;
 #pragma unroll
             for (int j = 0; j < DV; ++j) next[j] = vn < n ? (uint32_t)p.vedge[j * n + vn] * 4u : 0u;
-            variable_node<T, DV, PARITY>(p, ctrl, edge, llr, v, W, n, E, off);
+            variable_node<T, DV, PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E, off);
         }
     } else
     for (int v = threadIdx.x; v < n; v += blockDim.x) {
@@ -702,27 +702,27 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
         if (DV <= 12) {
             // exact-degree bodies: no per-edge predicates or branches inside
             switch (dv) {
-#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), PARITY>(p, ctrl, edge, llr, v, W, n, E); done = true; } break;
+#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E); done = true; } break;
                 LDPC_VCASE(0) LDPC_VCASE(1) LDPC_VCASE(2) LDPC_VCASE(3) LDPC_VCASE(4) LDPC_VCASE(5) LDPC_VCASE(6)
                 LDPC_VCASE(7) LDPC_VCASE(8) LDPC_VCASE(9) LDPC_VCASE(10) LDPC_VCASE(11) LDPC_VCASE(12)
 #undef LDPC_VCASE
             default: break;
             }
         } else if (dv == DV) {
-            variable_node<T, DV, PARITY>(p, ctrl, edge, llr, v, W, n, E);
+            variable_node<T, DV, PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E);
             done = true;
         }
-        if (!done) variable_node_any<T>(p, ctrl, edge, llr, v, W, dv, n, E);
+        if (!done) variable_node_any<T>(p, ctrl, gflag, edge, llr, v, W, dv, n, E);
     }
 }
 
 // parity-mode variant (posteriors and messages written through every iteration): kept out of line so that its
 // register needs do not shape the allocation of the throughput path
 template <class T, int DV, bool REGV>
-__device__ __noinline__ void variable_phase_parity(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr, int W,
+__device__ __noinline__ void variable_phase_parity(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
                                                    int n, int E, const uint8_t *vdeg)
 {
-    variable_phase<T, DV, true, REGV>(p, ctrl, edge, llr, W, n, E, vdeg);
+    variable_phase<T, DV, true, REGV>(p, ctrl, gflag, edge, llr, W, n, E, vdeg);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -762,7 +762,8 @@ __device__ __forceinline__ void emit_word(const KParams &p, Ctrl *ctrl, int s, i
 // thread of the CTA (contains barriers).
 template <class T>
 __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
-                                                 uint32_t fin, bool first, int n, int E, int W, long long frames)
+                                                 uint32_t fin, bool first, int n, int E, int W, long long frames,
+                                                 unsigned int trip, int buf)
 {
     const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
     const int nslots = W * T::LANES;
@@ -773,10 +774,10 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
     int old_it = 0;
     if (mine) {
         const int s = tid, w = s / T::LANES, lane = s % T::LANES;
-        was_over = (ctrl->gflag[w] >> lane) & 1u;
-        old_it = ctrl->it[s];
+        was_over = (ctrl->gflag[buf][w] >> lane) & 1u;
+        old_it = (int)(trip - ctrl->start[s]);
         if (!first)
-            p.iters[ctrl->fid[s]] = was_over ? -1 : (p.max_iter == 0 ? (int)((ctrl->failed[w] >> lane) & 1u) : old_it);
+            p.iters[ctrl->fid[s]] = was_over ? -1 : (p.max_iter == 0 ? (int)((ctrl->fail[buf][w] >> lane) & 1u) : old_it);
         // With claim_ahead the slot's next frame was taken from the queue (and its channel values pulled into L2)
         // when the previous one moved in; the atomic issued here is for the frame after, and its round trip
         // overlaps the passes below.
@@ -786,7 +787,6 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
         if (p.mc_mode == 2 && f >= 0)
             ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed, lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)f));
         ctrl->errs[s] = 0u;
-        atomicAnd(&ctrl->gflag[w], ~(1u << lane));
     }
     __syncthreads();
     if (p.mc_mode != 0 && emit) {
@@ -864,8 +864,8 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
         if (!first)
             for (int i = tid; i < E; i += nthreads) T::store_lane(&ew[i], lane, 0u);
     }
-    for (int s = 0; bad_slots; ++s, bad_slots >>= 1)
-        if (bad_slots & 1u) atomicOr(&ctrl->gflag[s / T::LANES], 1u << (s % T::LANES));
+    for (int s = 0; bad_slots; ++s, bad_slots >>= 1)  // judged by the coming trip's stop decision
+        if (bad_slots & 1u) atomicOr(&ctrl->gflag[buf == 2 ? 0 : buf + 1][s / T::LANES], 1u << (s % T::LANES));
     if (p.mc_mode != 0 && p.mc_pin_count > 0) {  // shortening: known positions pinned (PerfTest.cpp:410-414)
         __syncthreads();
         for (int i = tid; i < p.mc_pin_count; i += nthreads) {
@@ -881,7 +881,7 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
     __syncthreads();
     int ahead = -1;
     if (mine) {
-        const int s = tid, w = s / T::LANES, lane = s % T::LANES;
+        const int s = tid;
         if (!first && p.mc_mode != 0 && !was_over) {  // flagged frames are counted by their exact re-decode
             const unsigned int e = ctrl->errs[s];
             if (p.mc_frame_err) p.mc_frame_err[ctrl->fid[s]] = (unsigned short)min(e, 65535u);
@@ -891,8 +891,7 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
             atomicAdd(&p.mc_counters[3], (unsigned long long)old_it);
         }
         ctrl->fid[s] = ctrl->newfid[s];
-        ctrl->it[s] = 0;
-        atomicOr(&ctrl->fresh[w], 1u << lane);
+        ctrl->start[s] = trip + 1u;  // its first (initialising) variable phase runs in the coming trip
         if (p.claim_ahead) {
             ahead = queue_frame(p, claim, frames);
             ctrl->next[s] = ahead;
@@ -919,31 +918,28 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
 // Stop / continue decision of every slot, taken after the check phase (its votes are the syndrome of the state the
 // variable phase before it left): early termination after every iteration (ArrayLDPC_Decoder.cpp:164-167),
 // MAX_ITER (:63), decode_fixpoint's pre-check on the channel hard decisions (:443-450, iteration count 0), the
-// hard-decision-only mode (max_iter == 0) and lanes that left the packed range.  A frame that just moved in has
-// only had its initialisation, so its iteration count stays 0.  Returns the mask of stopping slots.
+// hard-decision-only mode (max_iter == 0) and lanes that left the packed range.  Every warp evaluates all slots
+// (lane = slot) from words nobody writes before the next barrier, so the mask of stopping slots is the same in
+// every thread and no barrier is needed to agree on it.
 template <class T>
-__device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, int W, unsigned int &trip)
+__device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, int W, unsigned int trip, int buf)
 {
-    const int tid = threadIdx.x, nslots = W * T::LANES;
-    // one thread per slot decides; the stop mask travels through shared memory (double buffered by trip
-    // parity so it can be cleared without another barrier)
-    if (tid < nslots) {
-        const int s = tid, w = s / T::LANES, lane = s % T::LANES;
-        if (ctrl->fid[s] >= 0) {
-            const bool fresh = (ctrl->fresh[w] >> lane) & 1u;
-            const int it = ctrl->it[s] + (fresh ? 0 : 1);
-            const bool pass = !((ctrl->fail[w] >> lane) & 1u);
-            const bool over = (ctrl->gflag[w] >> lane) & 1u;
-            ctrl->it[s] = it;
-            if (it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over) atomicOr(&ctrl->fin[trip & 1], 1u << s);
-        }
+    const int s = threadIdx.x & 31;
+    bool stop = false;
+    if (s < W * T::LANES && ctrl->fid[s] >= 0) {
+        const int w = s / T::LANES, lane = s % T::LANES;
+        const int it = (int)(trip - ctrl->start[s]);  // 0: the frame has only been initialised
+        const bool pass = !((ctrl->fail[buf][w] >> lane) & 1u);
+        const bool over = (ctrl->gflag[buf][w] >> lane) & 1u;
+        stop = it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over;
     }
-    __syncthreads();
-    const uint32_t fin = ctrl->fin[trip & 1];
-    if (tid < W) { ctrl->failed[tid] = ctrl->fail[tid]; ctrl->fail[tid] = 0u; ctrl->fresh[tid] = 0u; }
-    if (tid == 0) ctrl->fin[(trip + 1) & 1] = 0u;
-    ++trip;
-    if (fin) __syncthreads();  // the finish code reads what the threads above just wrote
+    const uint32_t fin = __ballot_sync(0xffffffffu, stop);
+    // the buffer the trip after next votes into (last read one decision ago, before two barriers)
+    if (threadIdx.x < MAX_W) {
+        const int clr = buf == 0 ? 2 : buf - 1;
+        ctrl->fail[clr][threadIdx.x] = 0u;
+        ctrl->gflag[clr][threadIdx.x] = 0u;
+    }
     return fin;
 }
 
@@ -987,14 +983,13 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
     const long long frames = p.count ? (long long)*p.count : p.frames;
 
     for (int i = tid; i < W * (E + n); i += nthreads) smem[i] = 0u;
-    if (tid < MAX_W) { ctrl->fail[tid] = 0u; ctrl->fresh[tid] = 0u; ctrl->gflag[tid] = 0u; ctrl->failed[tid] = 0u; }
+    if (tid < MAX_W)
+        for (int b = 0; b < 3; ++b) { ctrl->fail[b][tid] = 0u; ctrl->gflag[b][tid] = 0u; }
     if (tid < MAX_SLOTS) {
-        ctrl->fid[tid] = -1; ctrl->it[tid] = 0; ctrl->newfid[tid] = -1;
+        ctrl->fid[tid] = -1; ctrl->start[tid] = 0u; ctrl->newfid[tid] = -1;
         ctrl->next[tid] = (p.claim_ahead && tid < nslots) ? queue_frame(p, atomicAdd(p.queue, 1ull), frames) : -1;
     }
-    if (tid < 2) ctrl->fin[tid] = 0u;
     __syncthreads();
-    unsigned int trip = 0;
 
     const int items = (W / NI) * m;  // (word-set group, check)
 #ifdef LDPC_PHASE_TIMING
@@ -1006,21 +1001,27 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
 
     uint32_t fin = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);  // slots to (re)fill
     bool first = true;
+    // trip t votes into buffer t % 3; `buf` is the buffer of the trip that ended last (what a refill reports from)
+    unsigned int trip = 0;
+    int buf = 2;
     for (;;) {
         if (fin) {
-            const int active = finish_and_refill<T>(p, ctrl, edge, llr, fin, first, n, E, W, frames);
+            // trip - 1 is the trip whose stop decision released the slots
+            const int active = finish_and_refill<T>(p, ctrl, edge, llr, fin, first, n, E, W, frames, trip - 1u, buf);
             if (active == 0) break;
             first = false;
         }
+        buf = buf == 2 ? 0 : buf + 1;
         LDPC_MARK(0);
-        if (p.post || p.v2c) variable_phase_parity<T, DV, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
-        else variable_phase<T, DV, false, REGV>(p, ctrl, edge, llr, W, n, E, vdeg_s);
+        if (p.post || p.v2c) variable_phase_parity<T, DV, REGV>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s);
+        else variable_phase<T, DV, false, REGV>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s);
         __syncthreads();
         LDPC_MARK(1);
-        check_phase<T, DC, REG, NI>(p, ctrl, edge, cdeg_s, items, m, E, W);
+        check_phase<T, DC, REG, NI>(p, ctrl->fail[buf], edge, cdeg_s, items, m, E, W);
         __syncthreads();
         LDPC_MARK(2);
-        fin = stop_decision<T>(p, ctrl, W, trip);
+        fin = stop_decision<T>(p, ctrl, W, trip, buf);
+        ++trip;
         LDPC_MARK(3);
     }
 #ifdef LDPC_PHASE_TIMING
