@@ -80,6 +80,10 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
 struct Plan {
     KernelChoice kernel;
     int W = 0, threads = 0, smem = 0;
+    // irregular codes: which variable / check every thread handles in pass k of the variable / check phase
+    // ([k][thread], 0xffff = none), see build_order()
+    uint16_t *d_vorder = nullptr, *d_corder = nullptr;
+    int vorder_k = 0, corder_k = 0;
 };
 
 }  // namespace ldpc
@@ -162,6 +166,53 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
     return LDPC_OK;
 }
 
+// Work distribution for irregular codes.  Nodes are grouped into units of up to 32 nodes of the same degree (a warp
+// that runs one unit executes one exact-degree body, no divergence); nodes keep their index order inside a degree
+// class, so a unit is mostly a run of consecutive nodes (coalesced table reads, conflict-free shared-memory access).
+// Units are dealt to the warps of the CTA longest-first onto the least loaded warp, so that all warps reach the
+// barrier that ends the phase at about the same time (a degree-11 variable of the 802.11 code costs four times a
+// degree-2 one).  Returns the [passes][threads] table, 0xffff = idle.
+static std::vector<uint16_t> build_order(const std::vector<int> &deg, int threads, double base_cost, int &passes)
+{
+    const int n = (int)deg.size(), warps = threads / 32;
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return deg[a] > deg[b]; });
+    struct Unit { int first, count, degree; };
+    std::vector<Unit> units;
+    for (int i = 0; i < n;) {
+        int j = i;
+        while (j < n && j - i < 32 && deg[idx[j]] == deg[idx[i]]) ++j;
+        units.push_back({i, j - i, deg[idx[i]]});
+        i = j;
+    }
+    passes = ((int)units.size() + warps - 1) / warps;
+    std::vector<double> load(warps, 0.0);
+    std::vector<int> used(warps, 0);
+    std::vector<uint16_t> table((size_t)passes * threads, 0xffffu);
+    for (const Unit &u : units) {  // already sorted by degree, largest first
+        int best = -1;
+        for (int w = 0; w < warps; ++w)
+            if (used[w] < passes && (best < 0 || load[w] < load[best])) best = w;
+        for (int l = 0; l < u.count; ++l) table[(size_t)used[best] * threads + best * 32 + l] = (uint16_t)idx[u.first + l];
+        used[best]++;
+        load[best] += base_cost + u.degree;
+    }
+    return table;
+}
+
+static int upload_order(const ldpc_decoder &d, Plan &pl)
+{
+    const ldpc_code &c = d.code;
+    std::vector<uint16_t> v = build_order(c.vdeg, pl.threads, 1.5, pl.vorder_k);
+    std::vector<uint16_t> k = build_order(c.cdeg, pl.threads, 0.0, pl.corder_k);
+    CUDA_TRY(cudaMalloc(&pl.d_vorder, v.size() * 2));
+    CUDA_TRY(cudaMalloc(&pl.d_corder, k.size() * 2));
+    CUDA_TRY(cudaMemcpy(pl.d_vorder, v.data(), v.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(pl.d_corder, k.data(), k.size() * 2, cudaMemcpyHostToDevice));
+    return LDPC_OK;
+}
+
 static int upload_tables(ldpc_decoder &d)
 {
     const ldpc_code &c = d.code;
@@ -206,6 +257,7 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     KParams p;
     std::memset(&p, 0, sizeof p);
     p.cdeg = d.d_cdeg; p.vdeg = d.d_vdeg; p.vedge = d.d_vedge;
+    p.vorder = pl.d_vorder; p.corder = pl.d_corder; p.vorder_k = pl.vorder_k; p.corder_k = pl.corder_k;
     p.n = c.n; p.m = c.m; p.E = c.dc_max * c.m; p.dc_max = c.dc_max; p.dv_max = c.dv_max;
     p.W = pl.W; p.max_iter = d.cfg.max_iter; p.precheck = d.cfg.precheck;
     p.inv_m = (uint32_t)((1ull << 32) / (unsigned)c.m) + 1u;
@@ -574,6 +626,8 @@ ldpc_decoder *ldpc_decoder_create(const ldpc_code *code, const ldpc_decoder_cfg 
     if ((st = ldpc::upload_tables(*d)) != LDPC_OK) return fail(st);
     if ((st = ldpc::make_plan(*d, 2, ldpc::pick_kernel<ldpc::Packed16>(d->code), cfg.threads, cfg.frames_per_cta, d->plan16)) != LDPC_OK) return fail(st);
     if ((st = ldpc::make_plan(*d, 1, ldpc::pick_kernel<ldpc::Scalar32>(d->code), cfg.threads, cfg.frames_per_cta, d->plan32)) != LDPC_OK) return fail(st);
+    if ((st = ldpc::upload_order(*d, d->plan16)) != LDPC_OK) return fail(st);
+    if ((st = ldpc::upload_order(*d, d->plan32)) != LDPC_OK) return fail(st);
     d->stats.threads = d->plan16.threads; d->stats.threads32 = d->plan32.threads;
     d->stats.frames_per_cta = d->plan16.W * 2; d->stats.frames_per_cta32 = d->plan32.W;
     d->stats.smem_bytes = d->plan16.smem; d->stats.smem_bytes32 = d->plan32.smem;
@@ -594,7 +648,8 @@ void ldpc_decoder_destroy(ldpc_decoder *d)
     }
     if (d->s_in) cudaStreamDestroy(d->s_in);
     if (d->s_out) cudaStreamDestroy(d->s_out);
-    cudaFree(d->d_cdeg); cudaFree(d->d_vdeg); cudaFree(d->d_vedge); cudaFree(d->d_queue);
+    cudaFree(d->d_cdeg); cudaFree(d->d_vdeg); cudaFree(d->d_vedge);
+    cudaFree(d->plan16.d_vorder); cudaFree(d->plan16.d_corder); cudaFree(d->plan32.d_vorder); cudaFree(d->plan32.d_corder); cudaFree(d->d_queue);
     cudaFree(d->d_fb_index); cudaFree(d->d_fb_count); cudaFree(d->d_fb_total);
     cudaFree(d->d_mc_pow); cudaFree(d->d_mc_cw); cudaFree(d->d_mc_info); cudaFree(d->d_mc_pin);
     cudaFree(d->d_mc_iters); cudaFree(d->d_mc_ferr); cudaFree(d->d_mc_counters); cudaFree(d->d_mc_llr);

@@ -38,6 +38,11 @@ struct KParams {
     const uint8_t *vdeg;    // [n]
     const uint16_t *vedge;  // [dv_max][n]  word index (slot*m + check) of edge j of variable v
     int n, m, E, dc_max, dv_max;  // E = dc_max*m words per word set (slot-major, holes for short rows)
+    // irregular codes: node handled by thread t in pass k of the variable / check phase = order[k*blockDim + t]
+    // (0xffff: none).  A warp's 32 nodes in one pass have the same degree and the passes are dealt so that all
+    // warps carry about the same work (ldpc_decoder.cu: build_order).
+    const uint16_t *vorder, *corder;
+    int vorder_k, corder_k;
     // schedule
     int W;         // word sets per CTA
     int max_iter;  // MAX_ITER; 0 = hard decision + syndrome only (iters output: 0 pass, 1 fail)
@@ -494,6 +499,47 @@ __device__ __forceinline__ void check_phase(const KParams &p, uint32_t *fail, ui
                                             int items, int m, int E, int W)
 {
     const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
+    if (!REG) {
+        // irregular code: the checks of a warp's pass have one degree (p.corder), one group of NI word sets at a time
+        for (int wg = 0; wg < W / NI; ++wg) {
+            uint32_t mine[NI];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) mine[j] = 0u;
+            uint32_t cnext = p.corder[tid];
+            for (int k = 0; k < p.corder_k; ++k) {
+                const int c = (int)cnext;
+                if (k + 1 < p.corder_k) cnext = p.corder[(k + 1) * nthreads + tid];
+                if (c == 0xffff) continue;
+                uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
+                const int d = cdeg_s[c];
+                uint32_t fb[NI];
+#pragma unroll
+                for (int j = 0; j < NI; ++j) fb[j] = 0u;
+                bool done = false;
+                if (DC <= 16) {
+                    // exact-degree bodies: no per-edge predicates or branches inside
+                    switch (d) {
+#define LDPC_CCASE(D) case D: if (D <= DC) { check_nodes<T, (D <= DC ? D : 2), NI>(e0, m, E, fb); done = true; } break;
+                        LDPC_CCASE(2) LDPC_CCASE(3) LDPC_CCASE(4) LDPC_CCASE(5) LDPC_CCASE(6) LDPC_CCASE(7) LDPC_CCASE(8)
+                        LDPC_CCASE(9) LDPC_CCASE(10) LDPC_CCASE(11) LDPC_CCASE(12) LDPC_CCASE(13) LDPC_CCASE(14)
+                        LDPC_CCASE(15) LDPC_CCASE(16)
+#undef LDPC_CCASE
+                    default: break;
+                    }
+                }
+                if (!done)  // the loader rejects checks of degree < 2
+                    for (int j = 0; j < NI; ++j) fb[j] = check_node_any<T, DC>(e0 + (size_t)j * E, m, d);
+#pragma unroll
+                for (int j = 0; j < NI; ++j) mine[j] |= fb[j];
+            }
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                const uint32_t r = __reduce_or_sync(0xffffffffu, mine[j]);
+                if (lane_id == 0 && r) atomicOr(&fail[wg * NI + j], r);
+            }
+        }
+        return;
+    }
     // When the CTA holds a single word-set group (W == NI) every item votes for the same NI word sets: the
     // thread ORs its items' verdicts in registers and the warp reduces once, after the loop.
     const bool one_group = (W == NI);
@@ -510,26 +556,7 @@ __device__ __forceinline__ void check_phase(const KParams &p, uint32_t *fail, ui
         if (valid) {
             wg = (int)__umulhi((uint32_t)i, p.inv_m);
             const int c = i - wg * m;
-            uint32_t *e0 = edge + (size_t)(wg * NI) * E + c;
-            if (REG) {
-                check_nodes<T, DC, NI>(e0, m, E, fb);
-            } else {
-                const int d = cdeg_s[c];
-                bool done = false;
-                if (DC <= 16) {
-                    // exact-degree bodies: no per-edge predicates or branches inside
-                    switch (d) {
-#define LDPC_CCASE(D) case D: if (D <= DC) { check_nodes<T, (D <= DC ? D : 2), NI>(e0, m, E, fb); done = true; } break;
-                        LDPC_CCASE(2) LDPC_CCASE(3) LDPC_CCASE(4) LDPC_CCASE(5) LDPC_CCASE(6) LDPC_CCASE(7) LDPC_CCASE(8)
-                        LDPC_CCASE(9) LDPC_CCASE(10) LDPC_CCASE(11) LDPC_CCASE(12) LDPC_CCASE(13) LDPC_CCASE(14)
-                        LDPC_CCASE(15) LDPC_CCASE(16)
-#undef LDPC_CCASE
-                    default: break;
-                    }
-                }
-                if (!done)  // the loader rejects checks of degree < 2
-                    for (int j = 0; j < NI; ++j) fb[j] = check_node_any<T, DC>(e0 + (size_t)j * E, m, d);
-            }
+            check_nodes<T, DC, NI>(edge + (size_t)(wg * NI) * E + c, m, E, fb);
         }
         if (one_group) {
 #pragma unroll
@@ -695,24 +722,29 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
             for (int j = 0; j < DV; ++j) next[j] = vn < n ? (uint32_t)p.vedge[j * n + vn] * 4u : 0u;
             variable_node<T, DV, PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E, off);
         }
-    } else
-    for (int v = threadIdx.x; v < n; v += blockDim.x) {
-        const int dv = vdeg[v];
-        bool done = false;
-        if (DV <= 12) {
-            // exact-degree bodies: no per-edge predicates or branches inside
-            switch (dv) {
+    } else {
+        uint32_t vnext = p.vorder[threadIdx.x];
+        for (int k = 0; k < p.vorder_k; ++k) {
+            const int v = (int)vnext;
+            if (k + 1 < p.vorder_k) vnext = p.vorder[(k + 1) * blockDim.x + threadIdx.x];
+            if (v == 0xffff) continue;
+            const int dv = vdeg[v];
+            bool done = false;
+            if (DV <= 12) {
+                // exact-degree bodies: no per-edge predicates or branches inside
+                switch (dv) {
 #define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E); done = true; } break;
-                LDPC_VCASE(0) LDPC_VCASE(1) LDPC_VCASE(2) LDPC_VCASE(3) LDPC_VCASE(4) LDPC_VCASE(5) LDPC_VCASE(6)
-                LDPC_VCASE(7) LDPC_VCASE(8) LDPC_VCASE(9) LDPC_VCASE(10) LDPC_VCASE(11) LDPC_VCASE(12)
+                    LDPC_VCASE(0) LDPC_VCASE(1) LDPC_VCASE(2) LDPC_VCASE(3) LDPC_VCASE(4) LDPC_VCASE(5) LDPC_VCASE(6)
+                    LDPC_VCASE(7) LDPC_VCASE(8) LDPC_VCASE(9) LDPC_VCASE(10) LDPC_VCASE(11) LDPC_VCASE(12)
 #undef LDPC_VCASE
-            default: break;
+                default: break;
+                }
+            } else if (dv == DV) {
+                variable_node<T, DV, PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E);
+                done = true;
             }
-        } else if (dv == DV) {
-            variable_node<T, DV, PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E);
-            done = true;
+            if (!done) variable_node_any<T>(p, ctrl, gflag, edge, llr, v, W, dv, n, E);
         }
-        if (!done) variable_node_any<T>(p, ctrl, gflag, edge, llr, v, W, dv, n, E);
     }
 }
 
