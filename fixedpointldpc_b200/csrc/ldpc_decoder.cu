@@ -673,17 +673,21 @@ int ldpc_decode_batch(ldpc_decoder *d, const int32_t *llr, size_t frames, int32_
     CUDA_TRY(cudaSetDevice(d->device));
     const ldpc_code &c = d->code;
     const size_t nw32 = (c.n + 31) / 32, vsz = (size_t)c.dc_max * c.m;
-    // chunks large enough to fill every frame slot of the device a few times over, small enough that the
-    // copies of one chunk hide behind the decode of its neighbours (pinned host memory makes them asynchronous)
+    // Chunked pipeline: the H2D copy of chunk i+1, the decode of chunk i and the D2H copy of chunk i-1 overlap
+    // (pinned host memory makes the copies asynchronous).  The first chunk is one frame per slot so that the
+    // decode starts after a short copy; chunks then grow by half (the copy engine outruns the decoder by more than
+    // that) up to a few frames per slot, which keeps the idle slots at the end of every launch a small share.
     const size_t slots = (size_t)d->sm_count * d->plan16.kernel.ctas_per_sm * d->plan16.W * 2;
-    size_t chunk = std::max<size_t>(slots * 4, 8192);
-    if (post || v2c) chunk = std::max<size_t>(slots, 1024);  // parity-mode outputs are large
-    chunk = std::min(chunk, frames);
-    int rc = ldpc::ensure_staging(*d, chunk, post != nullptr, v2c != nullptr);
+    size_t max_chunk = std::max<size_t>(slots * 4, 4096), first_chunk = std::max<size_t>(slots, 1024);
+    if (post || v2c) max_chunk = first_chunk = std::max<size_t>(slots, 1024);  // parity-mode outputs are large
+    max_chunk = std::min(max_chunk, frames);
+    first_chunk = std::min(first_chunk, max_chunk);
+    int rc = ldpc::ensure_staging(*d, max_chunk, post != nullptr, v2c != nullptr);
     if (rc != LDPC_OK) return rc;
     cudaStream_t sk = d->stream;
     size_t index = 0;
-    for (size_t base = 0; base < frames; base += chunk, ++index) {
+    size_t chunk = first_chunk;
+    for (size_t base = 0; base < frames; base += chunk, chunk = std::min(max_chunk, chunk + chunk / 2), ++index) {
         const size_t cnt = std::min(chunk, frames - base);
         const int b = (int)(index & 1);
         if (index >= 2) CUDA_TRY(cudaStreamWaitEvent(d->s_in, d->ev_k[b], 0));   // decode of chunk i-2 consumed this buffer
