@@ -40,6 +40,8 @@ WORKLOADS = {
     "a24": ("array p=47 r=24 n=2209 (H_array_p47_r24_forward), FRAC_WIDTH=4, MAX_ITER=30", 3.0, 6.0, None, 1 << 15),
 }
 PRECHECK = {"wifi": False, "a5": True, "c79": False, "a24": True}  # decode_general_fp vs decode_fixpoint
+# frames per host core for the cpu_baseline leg of the GPU arm: about 10 s of the reference decoder at 30 iterations
+CPU_SAMPLE_PER_CORE = {"wifi": 4096, "a5": 3072, "c79": 3072, "a24": 384}
 
 
 def channel_rate(code_name, code):
@@ -378,7 +380,7 @@ def run_gpu_arm(args):
     }
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        sample = args.cpu_frames_per_core * cores
+        sample = min(frames, (args.cpu_baseline_frames_per_core or CPU_SAMPLE_PER_CORE[args.code]) * cores)
         llr_host = llr16[:sample].to(torch.int32).cpu().numpy()
         wall, cpu_iters, kind = cpu_decode(args.code, code, llr_host, cores)
         step_device(llr16)
@@ -407,7 +409,9 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--frames-per-cta", type=int, default=0)
     ap.add_argument("--e2e-frames", type=int, default=1 << 16)
-    ap.add_argument("--cpu-frames-per-core", type=int, default=256)
+    ap.add_argument("--cpu-frames-per-core", type=int, default=256, help="--impl reference: frames per core and step")
+    ap.add_argument("--cpu-baseline-frames-per-core", type=int, default=0,
+                    help="GPU arm: frames per core of the cpu_baseline leg (default: about 10 s of CPU work)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
