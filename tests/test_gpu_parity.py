@@ -259,3 +259,36 @@ def test_packed_kernel_equals_int32_kernel_at_scale(fp, name, snr_db, frames, sc
     if scale > 1:
         assert d_auto.stats()["fallback_frames"] > 0
     d_auto.close(); d_32.close()
+
+
+@pytest.mark.parametrize("name,snr_db,precheck", [("wifi", 1.8, False), ("a5", 4.2, True), ("c79", 4.0, False)])
+def test_one_long_launch_equals_many_short_ones(fp, name, snr_db, precheck):
+    """A long queue makes every slot take its next frame (and prefetch its channel values) one frame early; a
+    short one does not.  40 000 frames in one device launch and the same frames in launches of 1 500 must agree
+    frame for frame (iteration counts and decoded bits), pre-check hits included."""
+    import torch
+    code = fp.codes.NAMED[name]()
+    rate = fp.codes.INFO_BITS[name] / code.n
+    frames, small = 40000, 1500
+    llr = channel_frames(code.n, rate, snr_db, frames, seed=77)
+    if precheck:
+        llr[::97] = np.abs(llr[::97]) + 1  # all-zero codeword, no channel error, no zero LLR (a zero decides 1): decode_fixpoint returns 0
+    dec = fp.Decoder(code, precheck=precheck)
+    d_llr = torch.from_numpy(llr.astype(np.int16)).cuda()
+
+    def run(first, count):
+        it = torch.full((count,), -7, dtype=torch.int32, device="cuda")
+        bits = torch.zeros((count, code.nw32), dtype=torch.int32, device="cuda")
+        dec.decode_device(d_llr[first:first + count].data_ptr(), 16, count, it.data_ptr(), bits.data_ptr())
+        dec.sync()
+        return it.cpu().numpy(), bits.cpu().numpy()
+
+    it_long, bits_long = run(0, frames)
+    assert it_long.min() >= 0 and len(np.unique(it_long)) > 3
+    if precheck:
+        assert (it_long[::97] == 0).all()
+    for first in range(0, frames, small * 9):  # a sample of short launches
+        it_s, bits_s = run(first, min(small, frames - first))
+        assert (it_s == it_long[first:first + len(it_s)]).all()
+        assert (bits_s == bits_long[first:first + len(it_s)]).all()
+    dec.close()
