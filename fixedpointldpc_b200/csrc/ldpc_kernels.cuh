@@ -1,6 +1,6 @@
 // ldpc_kernels.cuh -- sm_100a decode kernels of the fixed-point LDPC engine.
 //
-// One persistent CTA per SM keeps W "word sets" resident in shared memory for the whole life
+// Persistent CTAs (one, two or four per SM) keep W "word sets" resident in shared memory for the whole life
 // of the frames decoded in them: E edge messages + n channel values, one 32-bit word each.
 // A word holds one frame (Scalar32: exact int32 arithmetic) or two frames (Packed16: int16x2
 // lanes, 13-bit magnitude guard).  Every lane of every word set is an independent frame slot
@@ -16,7 +16,7 @@
 //                   in registers (XOR-ing the hard decisions on the way: the syndrome),
 //                   backward chain + combine fused with the write-back
 //   stop decision   early termination / max_iter / pre-check (:164-167, :443-450); stopping
-//                   frames leave (results from the bit array) and the next ones move in
+//                   frames leave (results from the channel words) and the next ones move in
 //
 // Message words in shared memory
 //   v2c (variable -> check): sign | hd | magnitude   (Scalar32: bit31 | bit30 | 30 bits,
