@@ -595,10 +595,11 @@ __device__ __forceinline__ void check_phase(const KParams &p, uint32_t *fail, ui
 // iteration's survive).
 // ------------------------------------------------------------------------------------------
 
-template <class T, int D, int NW, bool PARITY>
-__device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uint32_t *gflag, char *base, uint32_t stride,
-                                               const uint32_t *off, uint32_t *llr, int v, int w, int n)
+template <class T, int D, int NW, bool PARITY, bool ACC>
+__device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *gacc, char *base,
+                                               uint32_t stride, const uint32_t *off, uint32_t *llr, int v, int w, int n)
 {
+    // ACC: gacc[] is the thread's running OR of the message words of word sets w, w+1, tested once per phase
     uint32_t x[NW][D > 0 ? D : 1], pw[NW], hd[NW], guard[NW], lx[NW];
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
@@ -610,7 +611,7 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uin
             T::acc_sub(acc, x[i][j]);
         }
         pw[i] = T::template post_word<D>(acc, hd[i]);
-        guard[i] = 0;
+        guard[i] = ACC ? gacc[i] : 0u;
     }
 #pragma unroll
     for (int j = 0; j < D; j += 2)
@@ -630,7 +631,8 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uin
         }
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
-        if (T::guard_hit(guard[i])) atomicOr(&gflag[w + i], T::guard_lanes(guard[i]));
+        if (ACC) gacc[i] = guard[i];
+        else if (T::guard_hit(guard[i])) atomicOr(&gflag[w + i], T::guard_lanes(guard[i]));
         llr[(w + i) * n + v] = T::llr_with_hd(lx[i], hd[i]);
         if (PARITY) {
 #pragma unroll
@@ -655,8 +657,29 @@ __device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint
     char *base = reinterpret_cast<char *>(edge);
     const uint32_t stride = (uint32_t)E * 4u;
     int w = 0;
-    for (; w + 1 < W; w += 2, base += 2 * stride) variable_words<T, D, 2, PARITY>(p, ctrl, gflag, base, stride, off, llr, v, w, n);
-    if (w < W) variable_words<T, D, 1, PARITY>(p, ctrl, gflag, base, stride, off, llr, v, w, n);
+    for (; w + 1 < W; w += 2, base += 2 * stride)
+        variable_words<T, D, 2, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
+    if (w < W) variable_words<T, D, 1, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
+}
+
+// the same with the guard bits of the first two word sets (all there are for the named codes) OR-ed into the
+// thread's accumulators instead of tested per variable; pays off for the short regular variable nodes
+template <class T, int D, bool PARITY>
+__device__ __forceinline__ void variable_node_acc(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t (&gacc)[2], uint32_t *edge,
+                                                  uint32_t *llr, int v, int W, int n, int E, const uint32_t *off)
+{
+    char *base = reinterpret_cast<char *>(edge);
+    const uint32_t stride = (uint32_t)E * 4u;
+    if (W == 1) {
+        variable_words<T, D, 1, PARITY, true>(p, ctrl, gflag, gacc, base, stride, off, llr, v, 0, n);
+        return;
+    }
+    variable_words<T, D, 2, PARITY, true>(p, ctrl, gflag, gacc, base, stride, off, llr, v, 0, n);
+    int w = 2;
+    base += 2 * stride;
+    for (; w + 1 < W; w += 2, base += 2 * stride)
+        variable_words<T, D, 2, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
+    if (w < W) variable_words<T, D, 1, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
 }
 
 template <class T, int D, bool PARITY>
@@ -709,6 +732,7 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
                                                int n, int E, const uint8_t *vdeg)
 {
     if (REGV) {
+        uint32_t gacc[2] = {0u, 0u};  // guard bits of the thread's variables in word sets 0 and 1
         int v = threadIdx.x;
         uint32_t next[DV];
 #pragma unroll
@@ -720,8 +744,10 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
             const int vn = v + blockDim.x;
 #pragma unroll
             for (int j = 0; j < DV; ++j) next[j] = vn < n ? (uint32_t)p.vedge[j * n + vn] * 4u : 0u;
-            variable_node<T, DV, PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E, off);
+            variable_node_acc<T, DV, PARITY>(p, ctrl, gflag, gacc, edge, llr, v, W, n, E, off);
         }
+        if (T::guard_hit(gacc[0])) atomicOr(&gflag[0], T::guard_lanes(gacc[0]));
+        if (T::guard_hit(gacc[1])) atomicOr(&gflag[1], T::guard_lanes(gacc[1]));
     } else {
         uint32_t vnext = p.vorder[threadIdx.x];
         for (int k = 0; k < p.vorder_k; ++k) {
