@@ -35,10 +35,10 @@ struct KernelChoice {
     bool cdeg_in_smem = false, vdeg_in_smem = false;
 };
 
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N> static KernelChoice make_choice()
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA = 0> static KernelChoice make_choice()
 {
     KernelChoice k;
-    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N>;
+    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA>;
     k.max_threads = MAXT;
     k.ni = NI;
     k.ctas_per_sm = NCTA;
@@ -61,15 +61,18 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
     // uniform variable degree, which all three array codes have)
     // Launch shapes below were chosen by measurement on B200 (profiles/r01/launch_shape_sweep.txt): for the long
     // checks more, smaller CTAs with one chain per thread beat two interleaved chains per thread (fewer registers,
-    // half the unrolled code, four independent phase streams per SM); the short 802.11 checks prefer NI = 2.
+    // half the unrolled code, four independent phase streams per SM); the short 802.11 checks prefer interleaved
+    // chains, and with the compact word sets three of them fit a CTA (NI = 3: +5 % over NI = 2).
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 5 && c.m == 235 && c.n == 2209)          // array p47 r5
         return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209>();
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 24 && c.m == 1128 && c.n == 2209)        // array p47 r24
         return make_choice<T, 47, true, 24, 1, 576, 1, 1128, 2209>();
     if (regular && vregular && c.dc_max == 28 && c.dv_max == 4 && c.m == 316 && c.n == 2212)          // cut79
         return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212>();
-    if (c.dc_max == 8 && c.dv_max <= 12 && c.m == 972 && c.n == 1944)                                // 802.11n 1944 r1/2
-        return make_choice<T, 8, false, 12, 2, 512, 2, 972, 1944>();
+    int full = 0, last = 0;  // words per word set with the checks sorted by descending degree (see ldpc_decoder::e_words)
+    for (int d : c.cdeg) { full += (d >= c.dc_max - 1); last += (d == c.dc_max); }
+    if (c.dc_max == 8 && c.dv_max <= 12 && c.m == 972 && c.n == 1944 && full == 972 && last == 162)  // 802.11n 1944 r1/2
+        return make_choice<T, 8, false, 12, 3, 512, 2, 972, 1944, 7 * 972 + 162>();  // three word sets per CTA and thread
     // any other code: run-time dimensions
     if (regular && c.dc_max == 47 && c.dv_max <= 5) return make_choice<T, 47, true, 5, 1, 256, 4, 0, 0>();
     if (c.dc_max <= 8 && c.dv_max <= 12) return make_choice<T, 8, false, 12, 2, 512, 2, 0, 0>();
@@ -97,7 +100,13 @@ struct ldpc_decoder {
     cudaStream_t stream = nullptr;
     // device tables
     uint8_t *d_cdeg = nullptr, *d_vdeg = nullptr;
-    uint16_t *d_vedge = nullptr;
+    uint16_t *d_vedge = nullptr, *d_eorig = nullptr;
+    // Checks are renumbered by descending degree inside the engine: with the slot-major layout word(slot, check) =
+    // slot*m + check, the checks that have a slot-k edge are then 0..cnt_k-1 and the unused tail of the last slots
+    // needs no shared memory (802.11: 6 966 words per word set instead of 8*972).  dev_cdeg = degrees in that order,
+    // e_words = words per word set, d_eorig[word] = the reference's EdgeRAM index of the word (parity-mode dump).
+    std::vector<int> dev_cdeg;
+    int e_words = 0;
     unsigned long long *d_queue = nullptr;  // [2]: packed launch, int32 launch
     Plan plan16, plan32;
     // host-buffer path: two staging sets so the H2D copy of chunk i+1, the decode of chunk i and the D2H copy
@@ -129,7 +138,7 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
     const ldpc_code &c = d.code;
     if (!k.fn) { set_error("check degree > 64 or variable degree > 32: no kernel instantiation"); return LDPC_ERR_UNSUPPORTED; }
     if ((long long)c.dc_max * c.m > 65535) { set_error("dc_max*m exceeds the 16-bit edge address space"); return LDPC_ERR_UNSUPPORTED; }
-    const int per_w = (c.dc_max * c.m + c.n) * 4;  // messages + channel values
+    const int per_w = (d.e_words + c.n) * 4;  // messages + channel values
     // co-resident CTAs share the SM's shared memory (228 KB minus 1 KB reserved per CTA)
     const int sm_total = d.max_smem + 1024;
     const int tables = (k.cdeg_in_smem ? ((c.m + 15) & ~15) : 0) + (k.vdeg_in_smem ? ((c.n + 15) & ~15) : 0);
@@ -205,7 +214,7 @@ static int upload_order(const ldpc_decoder &d, Plan &pl)
 {
     const ldpc_code &c = d.code;
     std::vector<uint16_t> v = build_order(c.vdeg, pl.threads, 1.5, pl.vorder_k);
-    std::vector<uint16_t> k = build_order(c.cdeg, pl.threads, 0.0, pl.corder_k);
+    std::vector<uint16_t> k = build_order(d.dev_cdeg, pl.threads, 0.0, pl.corder_k);
     CUDA_TRY(cudaMalloc(&pl.d_vorder, v.size() * 2));
     CUDA_TRY(cudaMalloc(&pl.d_corder, k.size() * 2));
     CUDA_TRY(cudaMemcpy(pl.d_vorder, v.data(), v.size() * 2, cudaMemcpyHostToDevice));
@@ -216,15 +225,31 @@ static int upload_order(const ldpc_decoder &d, Plan &pl)
 static int upload_tables(ldpc_decoder &d)
 {
     const ldpc_code &c = d.code;
+    std::vector<int> order(c.m), inv(c.m);
+    for (int i = 0; i < c.m; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return c.cdeg[a] > c.cdeg[b]; });
+    for (int i = 0; i < c.m; ++i) inv[order[i]] = i;
+    d.dev_cdeg.resize(c.m);
     std::vector<uint8_t> cdeg(c.m), vdeg(c.n);
-    for (int i = 0; i < c.m; ++i) cdeg[i] = (uint8_t)c.cdeg[i];
+    for (int i = 0; i < c.m; ++i) { d.dev_cdeg[i] = c.cdeg[order[i]]; cdeg[i] = (uint8_t)d.dev_cdeg[i]; }
     for (int v = 0; v < c.n; ++v) vdeg[v] = (uint8_t)c.vdeg[v];
     std::vector<uint16_t> vedge((size_t)c.dv_max * c.n, 0);
+    d.e_words = 0;
     for (int v = 0; v < c.n; ++v)
         for (int j = 0; j < c.vdeg[v]; ++j) {
             int chk = c.vlist[(size_t)v * c.dv_max + j], slot = c.vslot[(size_t)v * c.dv_max + j];
-            vedge[(size_t)j * c.n + v] = (uint16_t)(slot * c.m + chk);
+            const int word = slot * c.m + inv[chk];
+            vedge[(size_t)j * c.n + v] = (uint16_t)word;
+            d.e_words = std::max(d.e_words, word + 1);
         }
+    std::vector<uint16_t> eorig((size_t)std::max(d.e_words, 1), 0xffffu);
+    for (int v = 0; v < c.n; ++v)
+        for (int j = 0; j < c.vdeg[v]; ++j) {
+            int chk = c.vlist[(size_t)v * c.dv_max + j], slot = c.vslot[(size_t)v * c.dv_max + j];
+            eorig[vedge[(size_t)j * c.n + v]] = (uint16_t)(slot * c.m + chk);
+        }
+    CUDA_TRY(cudaMalloc(&d.d_eorig, eorig.size() * 2));
+    CUDA_TRY(cudaMemcpy(d.d_eorig, eorig.data(), eorig.size() * 2, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&d.d_cdeg, cdeg.size()));
     CUDA_TRY(cudaMalloc(&d.d_vdeg, vdeg.size()));
     CUDA_TRY(cudaMalloc(&d.d_vedge, vedge.size() * 2));
@@ -258,7 +283,8 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     std::memset(&p, 0, sizeof p);
     p.cdeg = d.d_cdeg; p.vdeg = d.d_vdeg; p.vedge = d.d_vedge;
     p.vorder = pl.d_vorder; p.corder = pl.d_corder; p.vorder_k = pl.vorder_k; p.corder_k = pl.corder_k;
-    p.n = c.n; p.m = c.m; p.E = c.dc_max * c.m; p.dc_max = c.dc_max; p.dv_max = c.dv_max;
+    p.eorig = d.d_eorig;
+    p.n = c.n; p.m = c.m; p.E = d.e_words; p.dc_max = c.dc_max; p.dv_max = c.dv_max;
     p.W = pl.W; p.max_iter = d.cfg.max_iter; p.precheck = d.cfg.precheck;
     p.inv_m = (uint32_t)((1ull << 32) / (unsigned)c.m) + 1u;
     p.llr = llr; p.llr_bits = llr_bits; p.frames = frames;
@@ -648,7 +674,7 @@ void ldpc_decoder_destroy(ldpc_decoder *d)
     }
     if (d->s_in) cudaStreamDestroy(d->s_in);
     if (d->s_out) cudaStreamDestroy(d->s_out);
-    cudaFree(d->d_cdeg); cudaFree(d->d_vdeg); cudaFree(d->d_vedge);
+    cudaFree(d->d_cdeg); cudaFree(d->d_vdeg); cudaFree(d->d_vedge); cudaFree(d->d_eorig);
     cudaFree(d->plan16.d_vorder); cudaFree(d->plan16.d_corder); cudaFree(d->plan32.d_vorder); cudaFree(d->plan32.d_corder); cudaFree(d->d_queue);
     cudaFree(d->d_fb_index); cudaFree(d->d_fb_count); cudaFree(d->d_fb_total);
     cudaFree(d->d_mc_pow); cudaFree(d->d_mc_cw); cudaFree(d->d_mc_info); cudaFree(d->d_mc_pin);

@@ -36,8 +36,10 @@ struct KParams {
     // code
     const uint8_t *cdeg;    // [m]
     const uint8_t *vdeg;    // [n]
-    const uint16_t *vedge;  // [dv_max][n]  word index (slot*m + check) of edge j of variable v
-    int n, m, E, dc_max, dv_max;  // E = dc_max*m words per word set (slot-major, holes for short rows)
+    const uint16_t *vedge;  // [dv_max][n]  word index (slot*m + check) of edge j of variable v; checks are numbered
+                            //              by descending degree in here, so the words of a word set are 0..E-1
+    const uint16_t *eorig;  // [E]          the same word in the reference's numbering (EdgeRAM order of the v2c dump)
+    int n, m, E, dc_max, dv_max;  // E <= dc_max*m words per word set (slot-major)
     // irregular codes: node handled by thread t in pass k of the variable / check phase = order[k*blockDim + t]
     // (0xffff: none).  A warp's 32 nodes in one pass have the same degree and the passes are dealt so that all
     // warps carry about the same work (ldpc_decoder.cu: build_order).
@@ -643,7 +645,7 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uin
                 if (p.v2c) {
                     int *out = p.v2c + (size_t)f * p.dc_max * p.m;  // EdgeRAM order: [slot][check]
 #pragma unroll
-                    for (int j = 0; j < D; ++j) out[off[j] >> 2] = T::v2c_value(x[i][j], lane);
+                    for (int j = 0; j < D; ++j) out[p.eorig[off[j] >> 2]] = T::v2c_value(x[i][j], lane);
                 }
             }
         }
@@ -719,7 +721,7 @@ __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, 
             if (p.v2c)
                 for (int j = 0; j < dv; ++j) {
                     const uint32_t a = p.vedge[(size_t)j * n + v];
-                    p.v2c[(size_t)f * p.dc_max * p.m + a] = T::v2c_value(ew[a], lane);
+                    p.v2c[(size_t)f * p.dc_max * p.m + p.eorig[a]] = T::v2c_value(ew[a], lane);
                 }
         }
     }
@@ -1006,7 +1008,8 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
 //   DC   largest check degree, REG: every check has degree DC
 //   DV   largest variable degree with an exact body
 //   NI   word sets per thread in the check phase (W is a multiple of NI)
-//   M, N compile-time m and n of the named codes (0 = read them from the parameters)
+//   M, N compile-time m and n of the named codes (0 = read them from the parameters); EA: words per word set if
+//        that is less than DC*M (irregular named code)
 //   MAXT, NCTA  launch bounds: CTA size and co-resident CTAs per SM.  Co-resident CTAs drift out of phase, so
 //        one's latency-bound variable phase overlaps the other's ALU-bound check phase.
 //
@@ -1020,14 +1023,14 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
 // so a frame that stops costs one check phase more than the reference executes, and a converged frame is
 // found by the same two barriers per trip that the phases need anyway.
 // ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N>
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA>
 __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constant__ KParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x, nthreads = blockDim.x;
     // the named codes get their dimensions as compile-time constants: every k*m word offset of the check
     // phase then folds into the load/store immediate
-    const int n = N ? N : p.n, m = M ? M : p.m, E = M ? DC * M : p.E, W = p.W;
+    const int n = N ? N : p.n, m = M ? M : p.m, E = EA ? EA : (M ? DC * M : p.E), W = p.W;
     uint32_t *edge = smem;                 // [W][E]
     uint32_t *llr = edge + (size_t)W * E;  // [W][n] channel values (+ the hard decision of the last posterior)
     Ctrl *ctrl = reinterpret_cast<Ctrl *>(llr + (size_t)W * n);
