@@ -659,6 +659,10 @@ __device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint
     char *base = reinterpret_cast<char *>(edge);
     const uint32_t stride = (uint32_t)E * 4u;
     int w = 0;
+    if (D <= 12 && W == 3) {  // all three word sets of the CTA at once
+        variable_words<T, D, 3, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, 0, n);
+        return;
+    }
     for (; w + 1 < W; w += 2, base += 2 * stride)
         variable_words<T, D, 2, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
     if (w < W) variable_words<T, D, 1, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
