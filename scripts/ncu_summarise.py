@@ -39,8 +39,10 @@ def main():
     ap.add_argument("--frames", type=int, required=True, help="frames decoded by the captured launch")
     ap.add_argument("--iters", type=float, default=30.0, help="average iterations per frame in the captured launch")
     ap.add_argument("--round", default="r01")
+    ap.add_argument("--outdir", default=None, help="write here instead of profiles/<round> (e.g. gpurun_out/summaries on the GPU box)")
     args = ap.parse_args()
-    outdir = os.path.join(ROOT, "profiles", args.round)
+    outdir = args.outdir or os.path.join(ROOT, "profiles", args.round)
+    os.makedirs(outdir, exist_ok=True)
 
     raw = ncu(args.report, "raw")
     hdr, units, vals = raw[0], raw[1], raw[2]
