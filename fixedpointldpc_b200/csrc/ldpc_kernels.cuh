@@ -115,8 +115,6 @@ struct Scalar32 {
     static constexpr uint32_t MAG = 0x3fffffffu, SIGN = 0x80000000u, HD = 0x40000000u;
     static constexpr uint32_t ALL = 0xffffffffu;
 
-    __device__ static __forceinline__ uint32_t lane_mask(int) { return 0xffffffffu; }
-
     // magnitude part of sxor: min + max(0,10-(sum&255)>>2) - max(0,10-(diff&255)>>2)
     //                       = min + min(10,(diff&255)>>2) - min(10,(sum&255)>>2)
     __device__ static __forceinline__ uint32_t g(uint32_t a, uint32_t b)
@@ -189,8 +187,6 @@ struct Packed16 {
     static constexpr uint32_t GUARD = 0x60006000u;  // magnitude bits 13,14 of the un-flagged word
     static constexpr uint32_t ALL = 0xffffffffu;
     static constexpr int LIMIT = 1 << 13;
-
-    __device__ static __forceinline__ uint32_t lane_mask(int lane) { return lane ? 0xffff0000u : 0x0000ffffu; }
 
     __device__ static __forceinline__ uint32_t g(uint32_t a, uint32_t b)
     {
