@@ -815,6 +815,48 @@ __device__ __forceinline__ void emit_word(const KParams &p, Ctrl *ctrl, int s, i
     }
 }
 
+// One slot of a decode-from-memory launch: the decoded bits of the frame that leaves (the hard decisions its last
+// variable phase left in the channel words, 32 consecutive variables per ballot) and the channel values of the
+// frame that moves in -- same thread, same word, so no barrier in between; four loads in flight per thread.
+// `bits_out` / `src`: rows of the two frames (NULL: nothing to write / no frame).  Pointers advance by the CTA
+// size instead of being rebuilt per element.  Returns true if a value of this thread left the packed range.
+template <class T, class SRC>
+__device__ __forceinline__ bool swap_frame(uint32_t *lw, int lane, uint32_t *bits_out, const SRC *src, int n)
+{
+    constexpr int UNR = 4;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const bool leader = (tid & 31) == 0;
+    uint32_t *word = lw + tid;
+    uint32_t *bout = bits_out ? bits_out + (tid >> 5) : nullptr;
+    const SRC *in = src ? src + tid : nullptr;
+    bool any_bad = false;
+    for (int v0 = tid; v0 - tid < n; v0 += UNR * nthreads) {
+        int val[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) val[u] = (in && v0 + u * nthreads < n) ? (int)in[u * nthreads] : 0;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int v = v0 + u * nthreads;
+            if (v - tid < n) {  // the same for every thread of the CTA
+                const bool mine = v < n;
+                if (bout) {
+                    const uint32_t bits = __ballot_sync(0xffffffffu, mine && T::hd_bit(word[u * nthreads], lane));
+                    if (leader && mine) bout[u * (nthreads >> 5)] = bits;
+                }
+                if (mine) {
+                    bool bad;
+                    T::store_lane(&word[u * nthreads], lane, T::llr_lane(val[u], bad));
+                    any_bad |= bad;
+                }
+            }
+        }
+        word += UNR * nthreads;
+        if (bout) bout += UNR * (nthreads >> 5);
+        if (in) in += UNR * nthreads;
+    }
+    return any_bad;
+}
+
 // Results of the slots in `fin` (unless `first`), then the next frames move in: the lane's messages are cleared
 // and its channel values loaded or generated.  Zero messages make the next variable phase produce
 // post = LLR, v2c = LLR -- the reference's initialisation (ArrayLDPC_Decoder.cpp:45-61) -- for the new lane while
@@ -871,32 +913,13 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
         const int fo = emit ? ctrl->fid[s] : -1, fn = ctrl->newfid[s];
         uint32_t *ew = edge + (size_t)w * E, *lw = llr + (size_t)w * n;
         if (p.mc_mode == 0) {
-            // decoded bits of the frame that leaves (the hard decisions its last variable phase left in the channel
-            // words), then the channel values of the frame that moves in: same thread, same word, no barrier
-            constexpr int UNR = 4;  // loads in flight per thread
-            const int16_t *g16 = reinterpret_cast<const int16_t *>(p.llr) + (size_t)(fn >= 0 ? fn : 0) * n;
-            const int *g32 = reinterpret_cast<const int *>(p.llr) + (size_t)(fn >= 0 ? fn : 0) * n;
-            for (int base = 0; base < n; base += UNR * nthreads) {
-                int val[UNR];
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    const int v = base + u * nthreads + tid;
-                    val[u] = 0;
-                    if (v < n && fn >= 0) val[u] = p.llr_bits == 16 ? (int)g16[v] : g32[v];
-                }
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    if (base + u * nthreads < n) {  // uniform
-                        const int v = base + u * nthreads + tid;
-                        if (fo >= 0) emit_word(p, ctrl, s, fo, v, n, v < n ? T::hd_bit(lw[v], lane) : 0u);
-                        if (v < n) {
-                            bool bad;
-                            T::store_lane(&lw[v], lane, T::llr_lane(val[u], bad));
-                            if (bad) bad_slots |= 1u << s;
-                        }
-                    }
-                }
-            }
+            uint32_t *bits_out = (fo >= 0 && p.bits) ? p.bits + (size_t)fo * p.nw32 : nullptr;
+            bool bad;
+            if (p.llr_bits == 16)
+                bad = swap_frame<T>(lw, lane, bits_out, fn >= 0 ? reinterpret_cast<const int16_t *>(p.llr) + (size_t)fn * n : nullptr, n);
+            else
+                bad = swap_frame<T>(lw, lane, bits_out, fn >= 0 ? reinterpret_cast<const int *>(p.llr) + (size_t)fn * n : nullptr, n);
+            if (bad) bad_slots |= 1u << s;
         } else if (p.mc_mode == 1) {
             for (int q = tid; 4 * q < n; q += nthreads) {
                 float z[4] = {0.f, 0.f, 0.f, 0.f};
