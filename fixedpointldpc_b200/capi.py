@@ -20,7 +20,7 @@ OK, ERR_IO, ERR_FORMAT, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_NO_DE
 EXPORTS = (
     "ldpc_strerror", "ldpc_last_error", "ldpc_code_load", "ldpc_code_from_checks", "ldpc_code_array",
     "ldpc_code_free", "ldpc_code_dims", "ldpc_code_tables", "ldpc_code_rate", "ldpc_code_save",
-    "ldpc_decoder_cfg_default", "ldpc_decoder_create", "ldpc_decoder_destroy", "ldpc_decode_batch",
+    "ldpc_decoder_cfg_default", "ldpc_decoder_create", "ldpc_decoder_destroy", "ldpc_decode_batch", "ldpc_decode_batch_i16",
     "ldpc_decode_batch_device", "ldpc_decoder_sync", "ldpc_decoder_get_stats", "ldpc_device_count",
     "ldpc_mc_run", "ldpc_mc_run_device", "ldpc_mc_channel", "ldpc_hard_decision_batch",
     "ldpc_encode_batch", "ldpc_encode_batch_device", "ldpc_gen_load", "ldpc_gen_from_code", "ldpc_gen_save", "ldpc_gen_free", "ldpc_gen_dims", "ldpc_gen_indices", "ldpc_gen_encode",
@@ -91,6 +91,7 @@ def load_library():
     L.ldpc_decoder_create.argtypes = [vp, C.POINTER(DecoderCfg), ip]
     L.ldpc_decoder_destroy.argtypes = [vp]
     L.ldpc_decode_batch.argtypes = [vp, vp, C.c_size_t, vp, vp, vp, vp]
+    L.ldpc_decode_batch_i16.argtypes = [vp, vp, C.c_size_t, vp, vp, vp, vp]
     L.ldpc_decode_batch_device.argtypes = [vp, vp, C.c_int, C.c_size_t, vp, vp, vp, vp, vp]
     L.ldpc_decoder_sync.argtypes = [vp]
     L.ldpc_decoder_get_stats.argtypes = [vp, C.POINTER(DecoderStats)]
@@ -273,9 +274,23 @@ class Decoder:
                                                 _ptr(out["post"]), _ptr(out["v2c"])))
         return out
 
-    def decode_raw(self, llr_ptr, frames, iters_ptr, bits_ptr=None, post_ptr=None, v2c_ptr=None):
-        """Host-pointer call (pinned buffers for the end-to-end timing)."""
-        _check(load_library().ldpc_decode_batch(self._h, llr_ptr, frames, iters_ptr, bits_ptr, post_ptr, v2c_ptr))
+    def decode_raw(self, llr_ptr, frames, iters_ptr, bits_ptr=None, post_ptr=None, v2c_ptr=None, llr_bits=32):
+        """Host-pointer call (pinned buffers for the end-to-end timing); llr_bits = 32 (`const int *LLR`) or 16."""
+        fn = load_library().ldpc_decode_batch if llr_bits == 32 else load_library().ldpc_decode_batch_i16
+        _check(fn(self._h, llr_ptr, frames, iters_ptr, bits_ptr, post_ptr, v2c_ptr))
+
+    def decode_i16(self, llr, want_bits=True, want_post=False, want_v2c=False):
+        """llr: int16 [frames][n] host array (ldpc_decode_batch_i16).  Returns dict(iters, bits, post, v2c)."""
+        c = self.code
+        llr = np.ascontiguousarray(llr, np.int16).reshape(-1, c.n)
+        f = len(llr)
+        out = {"iters": np.zeros(f, np.int32),
+               "bits": np.zeros((f, c.nw32), np.uint32) if want_bits else None,
+               "post": np.zeros((f, c.n), np.int32) if want_post else None,
+               "v2c": np.zeros((f, c.dc_max, c.m), np.int32) if want_v2c else None}
+        _check(load_library().ldpc_decode_batch_i16(self._h, _ptr(llr), f, _ptr(out["iters"]), _ptr(out["bits"]),
+                                                    _ptr(out["post"]), _ptr(out["v2c"])))
+        return out
 
     def decode_device(self, llr_ptr, llr_bits, frames, iters_ptr, bits_ptr=None, post_ptr=None, v2c_ptr=None,
                       stream=None):

@@ -35,17 +35,34 @@ struct KernelChoice {
     bool cdeg_in_smem = false, vdeg_in_smem = false;
 };
 
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA = 0> static KernelChoice make_choice()
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA = 0, int ARRP = 0> static KernelChoice make_choice()
 {
     KernelChoice k;
-    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA>;
+    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA, ARRP>;
     k.max_threads = MAXT;
     k.ni = NI;
     k.ctas_per_sm = NCTA;
     // shared-memory copies of the degree tables (must mirror the kernel's REG / REGV conditions)
     k.cdeg_in_smem = !REG;
-    k.vdeg_in_smem = !(PREFETCH_VEDGE && M != 0 && REG && DV <= 8);
+    k.vdeg_in_smem = !(PREFETCH_VEDGE && M != 0 && REG && DV <= 8) && ARRP == 0;
     return k;
+}
+
+// Forward square array code (class ROM, ArrayLDPCMacro.h:42-82): n = p*p, m = r*p, variable b*p + j meets check
+// a*p + ((j - a*b) mod p) of every row group a and sits in slot b there.  Kernels instantiated with ARRP compute the
+// edge addresses from this formula, so it is verified edge by edge before one of them is chosen.
+static bool is_forward_array(const ldpc_code &c, int p)
+{
+    if (p <= 0 || c.n != p * p || c.m % p != 0 || c.dv_max != c.m / p || c.dc_max != p) return false;
+    for (int v = 0; v < c.n; ++v) {
+        if (c.vdeg[v] != c.dv_max) return false;
+        const int b = v / p, j = v % p;
+        for (int a = 0; a < c.dv_max; ++a) {
+            const int t = ((j - a * b) % p + p) % p;
+            if (c.vlist[(size_t)v * c.dv_max + a] != a * p + t || c.vslot[(size_t)v * c.dv_max + a] != b) return false;
+        }
+    }
+    return true;
 }
 
 // Exact instantiations for the four named codes plus a generic bucket.  NI = word sets interleaved per thread
@@ -63,10 +80,16 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
     // checks more, smaller CTAs with one chain per thread beat two interleaved chains per thread (fewer registers,
     // half the unrolled code, four independent phase streams per SM); the short 802.11 checks prefer interleaved
     // chains, and with the compact word sets three of them fit a CTA (NI = 3: +5 % over NI = 2).
-    if (regular && vregular && c.dc_max == 47 && c.dv_max == 5 && c.m == 235 && c.n == 2209)          // array p47 r5
+    if (regular && vregular && c.dc_max == 47 && c.dv_max == 5 && c.m == 235 && c.n == 2209) {        // array p47 r5
+        if (getenv("LDPC_A5_CLOSED") && is_forward_array(c, 47)) return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209, 0, 47>();
         return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209>();
-    if (regular && vregular && c.dc_max == 47 && c.dv_max == 24 && c.m == 1128 && c.n == 2209)        // array p47 r24
-        return make_choice<T, 47, true, 24, 1, 576, 1, 1128, 2209>();
+    }
+    if (regular && vregular && c.dc_max == 47 && c.dv_max == 24 && c.m == 1128 && c.n == 2209 && is_forward_array(c, 47))  // array p47 r24
+    {
+        // 576 and 640 threads get the same 96 registers; 512 threads get 128 (no spills in the chains)
+        if (getenv("LDPC_A24_512")) return make_choice<T, 47, true, 24, 1, 512, 1, 1128, 2209, 0, 47>();
+        return make_choice<T, 47, true, 24, 1, 640, 1, 1128, 2209, 0, 47>();
+    }
     if (regular && vregular && c.dc_max == 28 && c.dv_max == 4 && c.m == 316 && c.n == 2212)          // cut79
         return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212>();
     int full = 0, last = 0;  // words per word set with the checks sorted by descending degree (see ldpc_decoder::e_words)
@@ -170,7 +193,9 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
     if (want_threads > 0) best_t = std::min(k.max_threads, std::max(32, (want_threads / 32) * 32));
     out.kernel = k; out.W = W; out.threads = best_t;
     out.smem = W * per_w + (int)sizeof(Ctrl) + tables;
-    cudaError_t e = cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, out.smem);
+    // the attribute belongs to the kernel instantiation, not to this decoder: decoders that share an instantiation
+    // with different word-set counts would otherwise lower each other's limit
+    cudaError_t e = cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem);
     if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return LDPC_ERR_CUDA; }
     return LDPC_OK;
 }
@@ -313,6 +338,18 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     return LDPC_OK;
 }
 
+// list of the frames the packed kernel flagged: sized before a pipeline starts, never in the middle of one
+static int ensure_fallback_list(ldpc_decoder &d, size_t frames)
+{
+    if (d.fb_cap >= frames) return LDPC_OK;
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(d.d_fb_index);
+    d.d_fb_index = nullptr; d.fb_cap = 0;
+    CUDA_TRY(cudaMalloc(&d.d_fb_index, frames * sizeof(int)));
+    d.fb_cap = frames;
+    return LDPC_OK;
+}
+
 static int decode_device(ldpc_decoder &d, const void *llr, int llr_bits, long long frames, int *iters,
                          uint32_t *bits, int *post, int *v2c, cudaStream_t st, const KParams *mc = nullptr)
 {
@@ -329,12 +366,9 @@ static int decode_device(ldpc_decoder &d, const void *llr, int llr_bits, long lo
     if (rc != LDPC_OK || d.cfg.precision == 16) return rc;
     // Exact int32 re-decode of the flagged frames, in place and without a host round trip: the
     // second launch reads the frame list and its length from device memory.
-    if (d.fb_cap < (size_t)frames) {
-        CUDA_TRY(cudaStreamSynchronize(st));
-        cudaFree(d.d_fb_index);
-        d.d_fb_index = nullptr; d.fb_cap = 0;
-        CUDA_TRY(cudaMalloc(&d.d_fb_index, (size_t)frames * sizeof(int)));
-        d.fb_cap = (size_t)frames;
+    if (d.fb_cap < (size_t)frames) {  // device API with a larger batch than any before (the host pipeline sizes it up front)
+        int rc2 = ensure_fallback_list(d, (size_t)frames);
+        if (rc2 != LDPC_OK) return rc2;
     }
     CUDA_TRY(cudaMemsetAsync(d.d_fb_count, 0, sizeof(int), st));
     collect_flagged<<<(unsigned)((frames + 255) / 256), 256, 0, st>>>(iters, frames, d.d_fb_index, d.d_fb_count, d.d_fb_total);
@@ -469,7 +503,7 @@ static int ensure_staging(ldpc_decoder &d, size_t frames, bool post, bool v2c)
         if (v2c) CUDA_TRY(cudaMalloc(&d.d_v2c[b], cap * (size_t)c.dc_max * c.m * sizeof(int)));
     }
     d.cap_frames = cap; d.cap_post = post; d.cap_v2c = v2c;
-    return LDPC_OK;
+    return ensure_fallback_list(d, cap);
 }
 
 }  // namespace ldpc
@@ -691,10 +725,12 @@ int ldpc_decode_batch_device(ldpc_decoder *d, const void *d_llr, int llr_bits, s
     return ldpc::decode_device(*d, d_llr, llr_bits, (long long)frames, d_iters, d_bits, d_post, d_v2c, st);
 }
 
-int ldpc_decode_batch(ldpc_decoder *d, const int32_t *llr, size_t frames, int32_t *iters, uint32_t *bits,
-                      int32_t *post, int32_t *v2c)
+static int decode_host(ldpc_decoder *d, const void *llr_v, int llr_bits, size_t frames, int32_t *iters, uint32_t *bits,
+                       int32_t *post, int32_t *v2c)
 {
-    if (!d || !llr || !iters) { ldpc::set_error("NULL decoder / llr / iters"); return LDPC_ERR_ARG; }
+    if (!d || !llr_v || !iters) { ldpc::set_error("NULL decoder / llr / iters"); return LDPC_ERR_ARG; }
+    const char *llr = static_cast<const char *>(llr_v);
+    const size_t esz = (size_t)llr_bits / 8;
     if (frames == 0) return LDPC_OK;
     CUDA_TRY(cudaSetDevice(d->device));
     const ldpc_code &c = d->code;
@@ -717,11 +753,11 @@ int ldpc_decode_batch(ldpc_decoder *d, const int32_t *llr, size_t frames, int32_
         const size_t cnt = std::min(chunk, frames - base);
         const int b = (int)(index & 1);
         if (index >= 2) CUDA_TRY(cudaStreamWaitEvent(d->s_in, d->ev_k[b], 0));   // decode of chunk i-2 consumed this buffer
-        CUDA_TRY(cudaMemcpyAsync(d->d_llr[b], llr + base * c.n, cnt * c.n * sizeof(int), cudaMemcpyHostToDevice, d->s_in));
+        CUDA_TRY(cudaMemcpyAsync(d->d_llr[b], llr + base * c.n * esz, cnt * c.n * esz, cudaMemcpyHostToDevice, d->s_in));
         CUDA_TRY(cudaEventRecord(d->ev_in[b], d->s_in));
         CUDA_TRY(cudaStreamWaitEvent(sk, d->ev_in[b], 0));
         if (index >= 2) CUDA_TRY(cudaStreamWaitEvent(sk, d->ev_out[b], 0));      // results of chunk i-2 have left
-        rc = ldpc::decode_device(*d, d->d_llr[b], 32, (long long)cnt, d->d_iters[b], bits ? d->d_bits[b] : nullptr,
+        rc = ldpc::decode_device(*d, d->d_llr[b], llr_bits, (long long)cnt, d->d_iters[b], bits ? d->d_bits[b] : nullptr,
                                  post ? d->d_post[b] : nullptr, v2c ? d->d_v2c[b] : nullptr, sk);
         if (rc != LDPC_OK) return rc;
         CUDA_TRY(cudaEventRecord(d->ev_k[b], sk));
@@ -735,6 +771,18 @@ int ldpc_decode_batch(ldpc_decoder *d, const int32_t *llr, size_t frames, int32_
     CUDA_TRY(cudaStreamSynchronize(d->s_out));
     CUDA_TRY(cudaStreamSynchronize(sk));
     return LDPC_OK;
+}
+
+int ldpc_decode_batch(ldpc_decoder *d, const int32_t *llr, size_t frames, int32_t *iters, uint32_t *bits,
+                      int32_t *post, int32_t *v2c)
+{
+    return decode_host(d, llr, 32, frames, iters, bits, post, v2c);
+}
+
+int ldpc_decode_batch_i16(ldpc_decoder *d, const int16_t *llr, size_t frames, int32_t *iters, uint32_t *bits,
+                          int32_t *post, int32_t *v2c)
+{
+    return decode_host(d, llr, 16, frames, iters, bits, post, v2c);
 }
 
 int ldpc_mc_run_device(ldpc_decoder *d, const ldpc_mc_cfg *cfg, size_t frames, uint16_t *d_frame_err,

@@ -61,9 +61,23 @@ __global__ void encode_kernel(const uint32_t *__restrict__ g, const int *__restr
     }
 }
 
+static void enc_release(EncTables &t)
+{
+    if (t.device >= 0) cudaSetDevice(t.device);
+    cudaFree(t.d_g); cudaFree(t.d_src); cudaFree(t.d_info); cudaFree(t.d_cw);
+    if (t.stream) cudaStreamDestroy(t.stream);
+    t = EncTables();
+}
+
+// Makes `device` current and (re)builds the device tables there.  A generator lives on one device at a time: a call
+// that names another device first releases everything the previous one holds (tables, staging, stream).
 static int enc_prepare(const ldpc_gen &g, int device, EncTables &t)
 {
-    if (t.d_g && t.device == device) return LDPC_OK;
+    if (t.d_g && t.device == device) {
+        if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return LDPC_ERR_CUDA; }
+        return LDPC_OK;
+    }
+    if (t.d_g || t.stream) enc_release(t);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); set_error("no CUDA device visible"); return LDPC_ERR_NO_DEVICE; }
     if (device < 0 || device >= ndev) { set_error("device ordinal out of range"); return LDPC_ERR_ARG; }
@@ -151,10 +165,7 @@ int ldpc_encode_batch(ldpc_gen *gen, int device, const uint8_t *info, size_t fra
 void ldpc_gen_release_device(ldpc_gen *gen)
 {
     if (!gen || !gen->dev) return;
-    ldpc::EncTables &t = gen->dev->t;
-    if (t.device >= 0) cudaSetDevice(t.device);
-    cudaFree(t.d_g); cudaFree(t.d_src); cudaFree(t.d_info); cudaFree(t.d_cw);
-    if (t.stream) cudaStreamDestroy(t.stream);
+    ldpc::enc_release(gen->dev->t);
     delete gen->dev;
     gen->dev = nullptr;
 }

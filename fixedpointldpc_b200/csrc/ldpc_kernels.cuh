@@ -776,13 +776,43 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
     }
 }
 
+// Forward square array codes in closed form (class ROM, ArrayLDPCMacro.h:42-82; the variable-phase address of
+// decode_fixpoint, ArrayLDPC_Decoder.cpp:583-589): variable v = b*P + j of column group b meets, in row group a,
+// check a*P + ((j - a*b) mod P), and sits in that check's slot b.  The word index b*m + a*P + t_a follows from
+// t_0 = j, t_(a+1) = t_a - b (mod P): two adds and an unsigned min per edge instead of a dependent table load from
+// L2 in a phase that is latency-bound (the host verifies the code against this formula before choosing the kernel).
+template <class T, int DV, int P, bool PARITY>
+__device__ __forceinline__ void variable_phase_array(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
+                                                     int W, int n, int m, int E)
+{
+    uint32_t gacc[2] = {0u, 0u};
+    constexpr uint32_t INV_P = (uint32_t)((1ull << 32) / P) + 1u;  // v / P == umulhi(v, INV_P) for v < 2^16
+    for (int v = threadIdx.x; v < n; v += blockDim.x) {
+        const uint32_t b = __umulhi((uint32_t)v, INV_P);
+        uint32_t u = ((uint32_t)v - b * P) * 4u;       // 4 * t_a
+        const uint32_t row = b * (uint32_t)m * 4u;      // byte offset of slot b
+        const uint32_t step = b * 4u;
+        uint32_t off[DV];
+#pragma unroll
+        for (int a = 0; a < DV; ++a) {
+            off[a] = row + (uint32_t)(a * P * 4) + u;
+            const uint32_t x = u - step;                // wraps to a huge value when t_a < b
+            u = min(x, x + (uint32_t)(P * 4));
+        }
+        variable_node_acc<T, DV, PARITY>(p, ctrl, gflag, gacc, edge, llr, v, W, n, E, off);
+    }
+    if (T::guard_hit(gacc[0])) atomicOr(&gflag[0], T::guard_lanes(gacc[0]));
+    if (W > 1 && T::guard_hit(gacc[1])) atomicOr(&gflag[1], T::guard_lanes(gacc[1]));
+}
+
 // parity-mode variant (posteriors and messages written through every iteration): kept out of line so that its
 // register needs do not shape the allocation of the throughput path
-template <class T, int DV, bool REGV>
+template <class T, int DV, bool REGV, int ARRP>
 __device__ __noinline__ void variable_phase_parity(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
-                                                   int n, int E, const uint8_t *vdeg)
+                                                   int n, int m, int E, const uint8_t *vdeg)
 {
-    variable_phase<T, DV, true, REGV>(p, ctrl, gflag, edge, llr, W, n, E, vdeg);
+    if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), true>(p, ctrl, gflag, edge, llr, W, n, m, E);
+    else variable_phase<T, DV, true, REGV>(p, ctrl, gflag, edge, llr, W, n, E, vdeg);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1033,6 +1063,7 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
 //   NI   word sets per thread in the check phase (W is a multiple of NI)
 //   M, N compile-time m and n of the named codes (0 = read them from the parameters); EA: words per word set if
 //        that is less than DC*M (irregular named code)
+//   ARRP forward square array code with this circulant size: edge addresses in closed form (variable_phase_array)
 //   MAXT, NCTA  launch bounds: CTA size and co-resident CTAs per SM.  Co-resident CTAs drift out of phase, so
 //        one's latency-bound variable phase overlaps the other's ALU-bound check phase.
 //
@@ -1046,7 +1077,7 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
 // so a frame that stops costs one check phase more than the reference executes, and a converged frame is
 // found by the same two barriers per trip that the phases need anyway.
 // ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA>
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA, int ARRP>
 __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constant__ KParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -1058,11 +1089,11 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
     uint32_t *llr = edge + (size_t)W * E;  // [W][n] channel values (+ the hard decision of the last posterior)
     Ctrl *ctrl = reinterpret_cast<Ctrl *>(llr + (size_t)W * n);
     // degree tables next to the control block (irregular codes dispatch on them once per node and phase)
-    constexpr bool REGV = PREFETCH_VEDGE && M != 0 && REG && DV <= 8;
+    constexpr bool REGV = PREFETCH_VEDGE && M != 0 && REG && DV <= 8 && ARRP == 0;
     uint8_t *cdeg_s = reinterpret_cast<uint8_t *>(ctrl + 1);
     uint8_t *vdeg_s = cdeg_s + (REG ? 0 : ((m + 15) & ~15));
     if (!REG) for (int i = tid; i < m; i += nthreads) cdeg_s[i] = p.cdeg[i];
-    if (!REGV) for (int i = tid; i < n; i += nthreads) vdeg_s[i] = p.vdeg[i];
+    if (!REGV && !ARRP) for (int i = tid; i < n; i += nthreads) vdeg_s[i] = p.vdeg[i];
     const int nslots = W * T::LANES;
     const long long frames = p.count ? (long long)*p.count : p.frames;
 
@@ -1097,7 +1128,8 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
         }
         buf = buf == 2 ? 0 : buf + 1;
         LDPC_MARK(0);
-        if (p.post || p.v2c) variable_phase_parity<T, DV, REGV>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s);
+        if (p.post || p.v2c) variable_phase_parity<T, DV, REGV, ARRP>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s);
+        else if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), false>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E);
         else variable_phase<T, DV, false, REGV>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s);
         __syncthreads();
         LDPC_MARK(1);

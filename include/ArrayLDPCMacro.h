@@ -132,13 +132,15 @@ public:
     int decode_general_fp(const int *LLR) { return run(LLR, 0); }
     int decode_fixpoint(const int *LLR)
     {
-        /* :443-450 pre-check, then the FSM gate :462/:488 */
-        if (!hardDecision(LLR)) return 0;
+        /* :443-450 pre-check, then the FSM gate :462/:488.  In state PCV both are one engine call: the precheck
+         * decoder returns 0 for a channel word that already satisfies H and leaves Posteriori_fp / EdgeRAM alone. */
         if (FSM.getState() == PCV) {
-            int it = run(LLR, 0);
+            int it = run(LLR, 1);
+            if (it == 0) return 0;                         /* :449, state stays PCV */
             FSM.setState(last_syndrome_fail ? C2V : IDLE); /* :619-630 */
             return it;
         }
+        if (!hardDecision(LLR)) return 0;
         if (FSM.getState() == C2V) {
             cerr << "FP_Decoder::decode_fixpoint: continuing a non-converged frame without setState(PCV) is not "
                     "supported by the GPU engine" << endl;
@@ -298,9 +300,16 @@ private:
         ensure_decoder();
         std::vector<uint32_t> bits((n_ + 31) / 32);
         int iters = 0;
-        int rc = ldpc_decode_batch(fixpoint ? dec_pre : dec_gen, LLR, 1, &iters, &bits[0], &Posteriori_fp[0], &EdgeRAM_fp[0]);
+        if (fixpoint) { post_tmp.resize(n_); edge_tmp.resize(EdgeRAM_fp.size()); }
+        int *post = fixpoint ? &post_tmp[0] : &Posteriori_fp[0], *edge = fixpoint ? &edge_tmp[0] : &EdgeRAM_fp[0];
+        int rc = ldpc_decode_batch(fixpoint ? dec_pre : dec_gen, LLR, 1, &iters, &bits[0], post, edge);
         if (rc != LDPC_OK) ldpc_facade::fail("FP_Decoder: decode failed", rc);
-        unpack(bits);
+        unpack(bits); /* a pre-check hit leaves the channel hard decisions here, like hardDecision (:276) */
+        if (fixpoint) {
+            if (iters == 0) return 0; /* Posteriori_fp / EdgeRAM keep the previous frame's values (quirk Q6) */
+            Posteriori_fp.swap(post_tmp);
+            EdgeRAM_fp.swap(edge_tmp);
+        }
         /* the kernel stops on the first passing syndrome, so only a frame that used every iteration can have
          * failed its last check; ask the engine (checkPost_fp, :619-630) */
         last_syndrome_fail = 0;
@@ -328,6 +337,7 @@ private:
     ldpc_decoder *dec_gen, *dec_pre;
     int n_, m_, dc_;
     std::vector<int> DecodedCodeword, TrueCodeword, TrueInfoBit, InfoIndex, Posteriori_fp, EdgeRAM_fp;
+    std::vector<int> post_tmp, edge_tmp;
     int BitError;
     int last_syndrome_fail;
     static const int Constant = int((5.0 / 8.0) * (1 << FRAC_WIDTH));

@@ -113,6 +113,12 @@ void ldpc_decoder_destroy(ldpc_decoder *dec);
 int ldpc_decode_batch(ldpc_decoder *dec, const int32_t *llr, size_t frames, int32_t *iters,
                       uint32_t *bits, int32_t *post, int32_t *v2c);
 
+/* The same call for callers that already hold 16-bit quantised LLRs (the reference's channel values stay far
+ * below 2^15: SURVEY.md 0.4): half the host->device bytes of the `const int *LLR` layout.  Results are identical
+ * to ldpc_decode_batch on the widened values. */
+int ldpc_decode_batch_i16(ldpc_decoder *dec, const int16_t *llr, size_t frames, int32_t *iters,
+                          uint32_t *bits, int32_t *post, int32_t *v2c);
+
 /* Same on DEVICE buffers, asynchronous on `stream` (a cudaStream_t, NULL = the decoder's own
  * stream).  llr_bits = 32 (int32) or 16 (int16) selects the input element type. */
 int ldpc_decode_batch_device(ldpc_decoder *dec, const void *d_llr, int llr_bits, size_t frames,

@@ -38,7 +38,7 @@ def main():
     ap.add_argument("tag")
     ap.add_argument("--frames", type=int, required=True, help="frames decoded by the captured launch")
     ap.add_argument("--iters", type=float, default=30.0, help="average iterations per frame in the captured launch")
-    ap.add_argument("--round", default="r01")
+    ap.add_argument("--round", default="r02")
     ap.add_argument("--outdir", default=None, help="write here instead of profiles/<round> (e.g. gpurun_out/summaries on the GPU box)")
     args = ap.parse_args()
     outdir = args.outdir or os.path.join(ROOT, "profiles", args.round)
@@ -103,6 +103,9 @@ def main():
     doc[args.code] = {
         "dram_bytes_per_frame": round(dram / args.frames, 1), "frames_in_capture": args.frames, "avg_iters": args.iters,
         "kernel_ms": num("gpu__time_duration.sum"),
+        # over the ELAPSED cycles of the launch (idle SM cycles and the tail included): what bench.py scales
+        "issue_elapsed_pct": num("sm__inst_executed.avg.pct_of_peak_sustained_elapsed"),
+        "alu_elapsed_pct": num("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed"),
         "alu_pipe_pct": num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
         "fma_pipe_pct": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
         "lsu_pipe_pct": num("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),

@@ -50,6 +50,8 @@ def _build_check(tmp, variant):
     ("a5", 1, "fixpoint", ["a5_4p5dB", "a5_9dB", "a5_2dB", "a5_9dB"]),
     ("a5", 1, "general", ["a5_4p5dB"]),
     ("c79", 3, "general", ["c79_4p5dB", "c79_2dB"]),
+    ("a24", 2, "fixpoint", ["a24_6dB", "a24_3dB"]),
+    ("a24", 2, "general", ["a24_6dB"]),
 ])
 def test_fp_decoder_class_frame_by_frame(tmp_path, fp, golden, name, variant, mode, tags):
     tmp = str(tmp_path)

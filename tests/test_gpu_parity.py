@@ -292,3 +292,27 @@ def test_one_long_launch_equals_many_short_ones(fp, name, snr_db, precheck):
         assert (it_s == it_long[first:first + len(it_s)]).all()
         assert (bits_s == bits_long[first:first + len(it_s)]).all()
     dec.close()
+
+
+@pytest.mark.parametrize("name", ["wifi", "a5"])
+def test_int16_host_entry_equals_int32_host_entry(fp, po, name):
+    """ldpc_decode_batch_i16 (half the host->device bytes) == ldpc_decode_batch on the widened values == the oracle,
+    including the chunked host pipeline (more frames than one chunk) and a frame that leaves the packed guard range."""
+    code = fp.codes.NAMED[name]()
+    t = tables_of(code)
+    rate = fp.codes.INFO_BITS[name] / code.n
+    llr = channel_frames(code.n, rate, 2.0 if name == "wifi" else 4.0, 9000, seed=99)
+    llr[7] *= 9          # leaves the 13-bit guard range but fits int16: exact int32 re-decode from the int16 input
+    llr = np.clip(llr, -32768, 32767)
+    dec = fp.Decoder(code, precheck=(name == "a5"))
+    a = dec.decode(llr, want_post=True)
+    b = dec.decode_i16(llr.astype(np.int16), want_post=True)
+    assert (a["iters"] == b["iters"]).all() and (a["bits"] == b["bits"]).all() and (a["post"] == b["post"]).all()
+    orc = po.Oracle(t)
+    for f in (0, 7, 8999):
+        it, bits, post, _ = orc.decode(llr[f], precheck=(name == "a5"))
+        assert it == b["iters"][f] and (fp.unpack_bits(b["bits"][f:f + 1], code.n)[0] == bits).all()
+        if it > 0:
+            assert (post == b["post"][f]).all()
+    assert dec.stats()["fallback_frames"] >= 1
+    dec.close()
