@@ -105,7 +105,8 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
 
 struct Plan {
     KernelChoice kernel;
-    int W = 0, threads = 0, smem = 0;
+    int W = 0, threads = 0, smem = 0;  // smem: word sets + control block + tables (stage rows come on top, per launch)
+    int smem_limit = 0;                // what one CTA may use with this many co-resident CTAs
     // irregular codes: which variable / check every thread handles in pass k of the variable / check phase
     // ([k][thread], 0xffff = none), see build_order()
     uint16_t *d_vorder = nullptr, *d_corder = nullptr;
@@ -165,7 +166,8 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
     // co-resident CTAs share the SM's shared memory (228 KB minus 1 KB reserved per CTA)
     const int sm_total = d.max_smem + 1024;
     const int tables = (k.cdeg_in_smem ? ((c.m + 15) & ~15) : 0) + (k.vdeg_in_smem ? ((c.n + 15) & ~15) : 0);
-    const int budget = (k.ctas_per_sm > 1 ? sm_total / k.ctas_per_sm - 1024 : d.max_smem) - (int)sizeof(Ctrl) - tables - 64;
+    const int limit = k.ctas_per_sm > 1 ? sm_total / k.ctas_per_sm - 1024 : d.max_smem;
+    const int budget = limit - (int)sizeof(Ctrl) - tables - 64;
     int W = std::min(budget / per_w, (int)MAX_W);
     if (want_slots > 0) {  // override, rounded up to whole groups of NI word sets
         int w = std::max(1, (want_slots + lanes - 1) / lanes);
@@ -192,7 +194,8 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
     }
     if (want_threads > 0) best_t = std::min(k.max_threads, std::max(32, (want_threads / 32) * 32));
     out.kernel = k; out.W = W; out.threads = best_t;
-    out.smem = W * per_w + (int)sizeof(Ctrl) + tables;
+    out.smem = W * per_w + 16 + (int)sizeof(Ctrl) + tables + 16;  // the control block and the stage rows are 16-byte aligned
+    out.smem_limit = limit;
     // the attribute belongs to the kernel instantiation, not to this decoder: decoders that share an instantiation
     // with different word-set counts would otherwise lower each other's limit
     cudaError_t e = cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem);
@@ -298,9 +301,17 @@ __global__ void collect_flagged(const int *iters, long long frames, int *index, 
     }
 }
 
+// fed launch (host pipeline): the frames arrive while the kernel runs, and finished chunks are announced to the host
+struct Feed {
+    const unsigned long long *avail;
+    unsigned int *done_count;
+    volatile unsigned int *done_flag;
+    int done_chunk;
+};
+
 static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, int llr_bits, long long frames,
                   int *iters, uint32_t *bits, int *post, int *v2c, const int *index, const int *count,
-                  cudaStream_t st, const KParams *mc = nullptr)
+                  cudaStream_t st, const KParams *mc = nullptr, const Feed *fed = nullptr)
 {
     if (frames <= 0) return LDPC_OK;
     const ldpc_code &c = d.code;
@@ -330,11 +341,22 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     // prefetched into L2); with a short queue that would starve the CTAs that start last.  The length of an
     // indirect queue (re-decode list) is only known on the device.
     p.claim_ahead = (!count && frames >= 4 * slots * grid) ? 1 : 0;
+    if (fed) { p.claim_ahead = 1; p.avail = fed->avail; p.done_count = fed->done_count; p.done_flag = fed->done_flag; p.done_chunk = fed->done_chunk; }
+    // The CTA keeps as many frames claimed ahead as it has slots, and the channel values of the first of them travel
+    // into stage rows in shared memory by TMA bulk copies while the CTA decodes (16-bit values from memory only; as
+    // many rows as the shared memory left over holds).
+    p.fifo_depth = (int)std::min<long long>(slots, MAX_FIFO);
+    p.stage_stride = ((c.n * 2 + 32) + 15) & ~15;
+    p.stage_rows = 0;
+    if (p.claim_ahead && !mc && llr_bits == 16 && !getenv("LDPC_NO_STAGE"))
+        p.stage_rows = std::max(0, std::min({(pl.smem_limit - pl.smem) / p.stage_stride, (int)MAX_STAGE, p.fifo_depth}));
+    const int smem = pl.smem + p.stage_rows * p.stage_stride;
     CUDA_TRY(cudaMemsetAsync(p.queue, 0, sizeof(unsigned long long), st));
-    pl.kernel.fn<<<grid, pl.threads, pl.smem, st>>>(p);
+    pl.kernel.fn<<<grid, pl.threads, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     d.stats.kernel_launches++;
     d.stats.grid = grid;
+    d.stats.stage_rows = p.stage_rows;
     return LDPC_OK;
 }
 

@@ -50,7 +50,18 @@ struct KParams {
     int max_iter;  // MAX_ITER; 0 = hard decision + syndrome only (iters output: 0 pass, 1 fail)
     uint32_t inv_m;  // floor(2^32 / m) + 1: i / m == umulhi(i, inv_m) for i < 2^16
     int precheck;  // decode_fixpoint's hardDecision pre-check
-    int claim_ahead;  // every slot takes its next frame index one frame early (long queues only)
+    int claim_ahead;  // the CTA keeps `fifo_depth` frame indices claimed ahead of need (long queues only)
+    int fifo_depth;   // 1..MAX_FIFO
+    int stage_rows;   // rows of shared memory that receive the channel values of the first claimed frames by
+                      // cp.async.bulk (TMA 1-D) while the CTA decodes; 0: the refill reads global memory itself
+    int stage_stride; // bytes per row buffer (16-byte multiple, >= one frame's values + 32)
+    // fed launches (host pipeline): frames [0, *avail) have arrived in `llr`; NULL: all of them
+    const unsigned long long *avail;
+    // fed launches: done_count[f / done_chunk] counts finished frames; the thread that completes a chunk sets the
+    // host-mapped done_flag[chunk], and the host then copies that chunk's results out while the kernel runs on
+    unsigned int *done_count;
+    volatile unsigned int *done_flag;
+    int done_chunk;
     // io
     const void *llr;  // [frames][n] int32 or int16
     int llr_bits;
@@ -176,6 +187,8 @@ struct Scalar32 {
         return (uint32_t)abs(val) | ((uint32_t)val & SIGN) | (val <= 0 ? HD : 0u);
     }
     __device__ static __forceinline__ void store_lane(uint32_t *word, int, uint32_t x) { *word = x; }
+    // all ones except in the lanes of word set w whose frame moved in this trip (`fresh`: one bit per slot)
+    __device__ static __forceinline__ uint32_t keep_mask(uint32_t fresh, int w) { return ((fresh >> w) & 1u) ? 0u : ALL; }
 };
 
 // Two frames per word (int16x2).  Exact as long as every |LLR|, |posterior| and |message| stays
@@ -280,6 +293,11 @@ struct Packed16 {
     {
         reinterpret_cast<uint16_t *>(word)[lane] = (uint16_t)x;
     }
+    __device__ static __forceinline__ uint32_t keep_mask(uint32_t fresh, int w)
+    {
+        const uint32_t b = fresh >> (2 * w);
+        return ~(((b & 1u) ? 0x0000ffffu : 0u) | ((b & 2u) ? 0xffff0000u : 0u));
+    }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -377,6 +395,8 @@ __device__ __forceinline__ uint32_t cw_bit(const KParams &p, long long f, int v)
 constexpr int MAX_W = 16;         // word sets per CTA
 constexpr bool PREFETCH_VEDGE = true;   // software-prefetch the next variable's edge addresses (costs registers)
 constexpr int MAX_SLOTS = 2 * MAX_W;
+constexpr int MAX_FIFO = 8;       // frame indices a CTA keeps claimed ahead of need
+constexpr int MAX_STAGE = 4;      // stage rows (channel values of claimed frames, filled by cp.async.bulk)
 
 struct Ctrl {
     // Votes of one trip, read by that trip's stop decision.  Every thread takes the decision for itself, without a
@@ -385,12 +405,44 @@ struct Ctrl {
     uint32_t fail[3][MAX_W];   // per word set: lanes with at least one unsatisfied check (check phase)
     uint32_t gflag[3][MAX_W];  // per word set: lanes that left the guard range (variable phase / load; Packed16)
     int fid[MAX_SLOTS];     // frame index decoded in the slot, -1 = idle
-    int next[MAX_SLOTS];    // frame the slot decodes after this one (taken from the queue one frame early), -1 = none
-    int newfid[MAX_SLOTS];  // frame moving into the slot during a refill
+    int newfid[MAX_SLOTS];  // frame that moved into the slot in this trip (valid from the refill pass to the header update)
     unsigned int start[MAX_SLOTS];  // trip in which the slot's frame moved in: iterations completed = trip - start
     uint32_t lehmer[MAX_SLOTS];  // Lehmer state before the slot's frame (MC mode 2)
     unsigned int errs[MAX_SLOTS];  // info-bit errors of the frames being finished (MC mode)
+    // Frames the CTA has claimed from the queue ahead of need: the entry with sequence number e lives in
+    // q_fid[e % fifo_depth]; entries q_head .. q_head + fifo_depth - 1 exist, and those below q_staged have their
+    // channel values in stage row e % stage_rows (copy in flight or landed; mbarrier bar[row], phase (e / rows) & 1).
+    // Written by thread 0 in the header update (between the two barriers of a trip), read by everybody after the
+    // second one -- so all threads see the same queue when they plan a refill.
+    int q_fid[MAX_FIFO];
+    unsigned int q_head, q_staged;
+    long long avail;                    // frames [0, avail) have arrived (fed launches; otherwise all)
+    unsigned long long bar[MAX_STAGE];  // mbarriers of the stage rows
 };
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------
 // check phase (ArrayLDPC_Decoder.cpp:66-118 + the syndrome of :296-333): NI independent check nodes of exact
@@ -593,10 +645,14 @@ __device__ __forceinline__ void check_phase(const KParams &p, uint32_t *fail, ui
 // iteration's survive).
 // ------------------------------------------------------------------------------------------
 
-template <class T, int D, int NW, bool PARITY, bool ACC>
+template <class T, int D, int NW, bool PARITY, bool ACC, bool MASK>
 __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *gacc, char *base,
-                                               uint32_t stride, const uint32_t *off, uint32_t *llr, int v, int w, int n)
+                                               uint32_t stride, const uint32_t *off, uint32_t *llr, int v, int w, int n,
+                                               uint32_t fresh)
 {
+    // MASK: lanes whose frame moved in this trip (`fresh`) read their incoming messages as zero, which makes this
+    // phase the reference's initialisation for them (post = LLR, v2c = LLR, ArrayLDPC_Decoder.cpp:45-61) -- the words
+    // still hold the previous frame's messages, nothing clears them
     // ACC: gacc[] is the thread's running OR of the message words of word sets w, w+1, tested once per phase
     uint32_t x[NW][D > 0 ? D : 1], pw[NW], hd[NW], guard[NW], lx[NW];
 #pragma unroll
@@ -606,6 +662,7 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uin
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             x[i][j] = *reinterpret_cast<uint32_t *>(base + i * stride + off[j]);
+            if (MASK) x[i][j] &= T::keep_mask(fresh, w + i);
             T::acc_sub(acc, x[i][j]);
         }
         pw[i] = T::template post_word<D>(acc, hd[i]);
@@ -648,67 +705,68 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uin
     }
 }
 
-template <class T, int D, bool PARITY>
+template <class T, int D, bool PARITY, bool MASK>
 __device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
-                                              int v, int W, int n, int E, const uint32_t *off)
+                                              int v, int W, int n, int E, const uint32_t *off, uint32_t fresh)
 {
     char *base = reinterpret_cast<char *>(edge);
     const uint32_t stride = (uint32_t)E * 4u;
     int w = 0;
     if (D <= 12 && W == 3) {  // all three word sets of the CTA at once
-        variable_words<T, D, 3, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, 0, n);
+        variable_words<T, D, 3, PARITY, false, MASK>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, 0, n, fresh);
         return;
     }
     for (; w + 1 < W; w += 2, base += 2 * stride)
-        variable_words<T, D, 2, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
-    if (w < W) variable_words<T, D, 1, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
+        variable_words<T, D, 2, PARITY, false, MASK>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n, fresh);
+    if (w < W) variable_words<T, D, 1, PARITY, false, MASK>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n, fresh);
 }
 
 // the same with the guard bits of the first two word sets (all there are for the named codes) OR-ed into the
 // thread's accumulators instead of tested per variable; pays off for the short regular variable nodes
-template <class T, int D, bool PARITY>
+template <class T, int D, bool PARITY, bool MASK>
 __device__ __forceinline__ void variable_node_acc(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t (&gacc)[2], uint32_t *edge,
-                                                  uint32_t *llr, int v, int W, int n, int E, const uint32_t *off)
+                                                  uint32_t *llr, int v, int W, int n, int E, const uint32_t *off, uint32_t fresh)
 {
     char *base = reinterpret_cast<char *>(edge);
     const uint32_t stride = (uint32_t)E * 4u;
     if (W == 1) {
-        variable_words<T, D, 1, PARITY, true>(p, ctrl, gflag, gacc, base, stride, off, llr, v, 0, n);
+        variable_words<T, D, 1, PARITY, true, MASK>(p, ctrl, gflag, gacc, base, stride, off, llr, v, 0, n, fresh);
         return;
     }
-    variable_words<T, D, 2, PARITY, true>(p, ctrl, gflag, gacc, base, stride, off, llr, v, 0, n);
+    variable_words<T, D, 2, PARITY, true, MASK>(p, ctrl, gflag, gacc, base, stride, off, llr, v, 0, n, fresh);
     int w = 2;
     base += 2 * stride;
     for (; w + 1 < W; w += 2, base += 2 * stride)
-        variable_words<T, D, 2, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
-    if (w < W) variable_words<T, D, 1, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
+        variable_words<T, D, 2, PARITY, false, MASK>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n, fresh);
+    if (w < W) variable_words<T, D, 1, PARITY, false, MASK>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n, fresh);
 }
 
-template <class T, int D, bool PARITY>
+template <class T, int D, bool PARITY, bool MASK>
 __device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
-                                              int v, int W, int n, int E)
+                                              int v, int W, int n, int E, uint32_t fresh)
 {
     uint32_t off[D > 0 ? D : 1];  // byte offsets of the D edge words inside a word set
 #pragma unroll
     for (int j = 0; j < D; ++j) off[j] = (uint32_t)p.vedge[j * n + v] * 4u;
-    variable_node<T, D, PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E, off);
+    variable_node<T, D, PARITY, MASK>(p, ctrl, gflag, edge, llr, v, W, n, E, off, fresh);
 }
 
 // any degree (slow path for degrees without an exact instantiation): two passes over the words
 template <class T>
 __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
-                                                  int v, int W, int dv, int n, int E)
+                                                  int v, int W, int dv, int n, int E, uint32_t fresh)
 {
     for (int w = 0; w < W; ++w) {
         uint32_t *ew = edge + (size_t)w * E;
+        const uint32_t keep = T::keep_mask(fresh, w);
         const uint32_t lx = T::llr_restore(llr[(size_t)w * n + v]);
         typename T::Acc acc = T::acc_init(lx);
-        for (int j = 0; j < dv; ++j) T::acc_sub(acc, ew[p.vedge[(size_t)j * n + v]]);
+        for (int j = 0; j < dv; ++j) T::acc_sub(acc, ew[p.vedge[(size_t)j * n + v]] & keep);
         uint32_t hd, guard = 0;
         const uint32_t pw = T::template post_word<64>(acc, hd);
         for (int j = 0; j < dv; ++j) {
             uint32_t *q = &ew[p.vedge[(size_t)j * n + v]];
-            const uint32_t a = T::v2c_signmag(pw, *q);
+            const uint32_t a = T::v2c_signmag(pw, *q & keep);
             guard |= a;
             *q = a | hd;
         }
@@ -729,9 +787,9 @@ __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, 
 
 // REGV: every variable has degree DV -- the edge addresses of the thread's next variable are fetched while the
 // current one is processed (the table lives in global memory / L2)
-template <class T, int DV, bool PARITY, bool REGV>
+template <class T, int DV, bool PARITY, bool REGV, bool MASK>
 __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
-                                               int n, int E, const uint8_t *vdeg)
+                                               int n, int E, const uint8_t *vdeg, uint32_t fresh)
 {
     if (REGV) {
         uint32_t gacc[2] = {0u, 0u};  // guard bits of the thread's variables in word sets 0 and 1
@@ -746,7 +804,7 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
             const int vn = v + blockDim.x;
 #pragma unroll
             for (int j = 0; j < DV; ++j) next[j] = vn < n ? (uint32_t)p.vedge[j * n + vn] * 4u : 0u;
-            variable_node_acc<T, DV, PARITY>(p, ctrl, gflag, gacc, edge, llr, v, W, n, E, off);
+            variable_node_acc<T, DV, PARITY, MASK>(p, ctrl, gflag, gacc, edge, llr, v, W, n, E, off, fresh);
         }
         if (T::guard_hit(gacc[0])) atomicOr(&gflag[0], T::guard_lanes(gacc[0]));
         if (T::guard_hit(gacc[1])) atomicOr(&gflag[1], T::guard_lanes(gacc[1]));
@@ -761,17 +819,17 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
             if (DV <= 12) {
                 // exact-degree bodies: no per-edge predicates or branches inside
                 switch (dv) {
-#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E); done = true; } break;
+#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), PARITY, MASK>(p, ctrl, gflag, edge, llr, v, W, n, E, fresh); done = true; } break;
                     LDPC_VCASE(0) LDPC_VCASE(1) LDPC_VCASE(2) LDPC_VCASE(3) LDPC_VCASE(4) LDPC_VCASE(5) LDPC_VCASE(6)
                     LDPC_VCASE(7) LDPC_VCASE(8) LDPC_VCASE(9) LDPC_VCASE(10) LDPC_VCASE(11) LDPC_VCASE(12)
 #undef LDPC_VCASE
                 default: break;
                 }
             } else if (dv == DV) {
-                variable_node<T, DV, PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E);
+                variable_node<T, DV, PARITY, MASK>(p, ctrl, gflag, edge, llr, v, W, n, E, fresh);
                 done = true;
             }
-            if (!done) variable_node_any<T>(p, ctrl, gflag, edge, llr, v, W, dv, n, E);
+            if (!done) variable_node_any<T>(p, ctrl, gflag, edge, llr, v, W, dv, n, E, fresh);
         }
     }
 }
@@ -781,9 +839,9 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
 // check a*P + ((j - a*b) mod P), and sits in that check's slot b.  The word index b*m + a*P + t_a follows from
 // t_0 = j, t_(a+1) = t_a - b (mod P): two adds and an unsigned min per edge instead of a dependent table load from
 // L2 in a phase that is latency-bound (the host verifies the code against this formula before choosing the kernel).
-template <class T, int DV, int P, bool PARITY>
+template <class T, int DV, int P, bool PARITY, bool MASK>
 __device__ __forceinline__ void variable_phase_array(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
-                                                     int W, int n, int m, int E)
+                                                     int W, int n, int m, int E, uint32_t fresh)
 {
     uint32_t gacc[2] = {0u, 0u};
     constexpr uint32_t INV_P = (uint32_t)((1ull << 32) / P) + 1u;  // v / P == umulhi(v, INV_P) for v < 2^16
@@ -799,7 +857,7 @@ __device__ __forceinline__ void variable_phase_array(const KParams &p, Ctrl *ctr
             const uint32_t x = u - step;                // wraps to a huge value when t_a < b
             u = min(x, x + (uint32_t)(P * 4));
         }
-        variable_node_acc<T, DV, PARITY>(p, ctrl, gflag, gacc, edge, llr, v, W, n, E, off);
+        variable_node_acc<T, DV, PARITY, MASK>(p, ctrl, gflag, gacc, edge, llr, v, W, n, E, off, fresh);
     }
     if (T::guard_hit(gacc[0])) atomicOr(&gflag[0], T::guard_lanes(gacc[0]));
     if (W > 1 && T::guard_hit(gacc[1])) atomicOr(&gflag[1], T::guard_lanes(gacc[1]));
@@ -809,14 +867,39 @@ __device__ __forceinline__ void variable_phase_array(const KParams &p, Ctrl *ctr
 // register needs do not shape the allocation of the throughput path
 template <class T, int DV, bool REGV, int ARRP>
 __device__ __noinline__ void variable_phase_parity(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
-                                                   int n, int m, int E, const uint8_t *vdeg)
+                                                   int n, int m, int E, const uint8_t *vdeg, uint32_t fresh)
 {
-    if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), true>(p, ctrl, gflag, edge, llr, W, n, m, E);
-    else variable_phase<T, DV, true, REGV>(p, ctrl, gflag, edge, llr, W, n, E, vdeg);
+    if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), true, true>(p, ctrl, gflag, edge, llr, W, n, m, E, fresh);
+    else variable_phase<T, DV, true, REGV, true>(p, ctrl, gflag, edge, llr, W, n, E, vdeg, fresh);
+}
+
+// throughput path: the masked instantiation runs only in trips in which a frame moved in
+template <class T, int DV, bool REGV, int ARRP>
+__device__ __forceinline__ void variable_phase_fast(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
+                                                    int n, int m, int E, const uint8_t *vdeg, uint32_t fresh)
+{
+    if (fresh) {
+        if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), false, true>(p, ctrl, gflag, edge, llr, W, n, m, E, fresh);
+        else variable_phase<T, DV, false, REGV, true>(p, ctrl, gflag, edge, llr, W, n, E, vdeg, fresh);
+    } else {
+        if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), false, false>(p, ctrl, gflag, edge, llr, W, n, m, E, 0u);
+        else variable_phase<T, DV, false, REGV, false>(p, ctrl, gflag, edge, llr, W, n, E, vdeg, 0u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // results of stopping frames, refill
+//
+// A trip of the main loop that has slots to serve (`want`: frames that stopped at the last decision, or idle slots
+// while the queue still has frames) runs
+//     refill pass     every thread plans the refill from the control block (same answer in every thread, no barrier):
+//                     results of the frames that leave, channel values of the frames that move in; ONE barrier
+//     variable phase  lanes that just received a frame read their messages as zero (`fresh` mask): nothing is cleared
+//     [barrier]
+//     header update   slot owners / thread 0, while the other warps start the check phase: slot headers, Monte-Carlo
+//                     counters, the queue of claimed frames, bulk copies of the next frames into the stage rows
+// so a refill costs one extra barrier, and the latencies of the queue atomic and of the channel values (TMA bulk copy
+// into shared memory, issued a whole trip before the values are needed) stay off the critical path.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2(const void *ptr)
 {
@@ -827,6 +910,12 @@ __device__ __forceinline__ void prefetch_l2(const void *ptr)
 __device__ __forceinline__ int queue_frame(const KParams &p, unsigned long long q, long long frames)
 {
     return q < (unsigned long long)frames ? (p.index ? p.index[q] : (int)q) : -1;
+}
+
+__device__ __forceinline__ long long frames_arrived(const KParams &p, long long frames)
+{
+    if (!p.avail) return frames;
+    return (long long)*reinterpret_cast<const volatile unsigned long long *>(p.avail);
 }
 
 // hard decisions of 32 consecutive variables of the frame `fo` that leaves slot s: packed bits and / or the
@@ -848,8 +937,9 @@ __device__ __forceinline__ void emit_word(const KParams &p, Ctrl *ctrl, int s, i
 // One slot of a decode-from-memory launch: the decoded bits of the frame that leaves (the hard decisions its last
 // variable phase left in the channel words, 32 consecutive variables per ballot) and the channel values of the
 // frame that moves in -- same thread, same word, so no barrier in between; four loads in flight per thread.
-// `bits_out` / `src`: rows of the two frames (NULL: nothing to write / no frame).  Pointers advance by the CTA
-// size instead of being rebuilt per element.  Returns true if a value of this thread left the packed range.
+// `bits_out` / `src`: rows of the two frames (NULL: nothing to write / no frame moves in, the words are left alone).
+// `src` points to global memory or to a stage row in shared memory.  Pointers advance by the CTA size instead of
+// being rebuilt per element.  Returns true if a value of this thread left the packed range.
 template <class T, class SRC>
 __device__ __forceinline__ bool swap_frame(uint32_t *lw, int lane, uint32_t *bits_out, const SRC *src, int n)
 {
@@ -873,7 +963,7 @@ __device__ __forceinline__ bool swap_frame(uint32_t *lw, int lane, uint32_t *bit
                     const uint32_t bits = __ballot_sync(0xffffffffu, mine && T::hd_bit(word[u * nthreads], lane));
                     if (leader && mine) bout[u * (nthreads >> 5)] = bits;
                 }
-                if (mine) {
+                if (mine && in) {
                     bool bad;
                     T::store_lane(&word[u * nthreads], lane, T::llr_lane(val[u], bad));
                     any_bad |= bad;
@@ -887,80 +977,152 @@ __device__ __forceinline__ bool swap_frame(uint32_t *lw, int lane, uint32_t *bit
     return any_bad;
 }
 
-// Results of the slots in `fin` (unless `first`), then the next frames move in: the lane's messages are cleared
-// and its channel values loaded or generated.  Zero messages make the next variable phase produce
-// post = LLR, v2c = LLR -- the reference's initialisation (ArrayLDPC_Decoder.cpp:45-61) -- for the new lane while
-// it runs an ordinary iteration for the lane's neighbour.  Returns the number of active slots.  Called by every
-// thread of the CTA (contains barriers).
-template <class T>
-__device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
-                                                 uint32_t fin, bool first, int n, int E, int W, long long frames,
-                                                 unsigned int trip, int buf)
+// Where the next wanting slot gets its frame from.  Called by every thread for the slots of `want` in ascending
+// order with the same running state, so all threads plan the same refill without exchanging anything:
+//   sync  the slot's owner claimed a frame for it just now (ctrl->newfid, after a barrier)
+//   else  the oldest entry of the CTA's queue of claimed frames, if it exists, is a frame, and its values are there
+//         (in a stage row, or -- fed launches -- already arrived in global memory); entries are taken in order, so
+//         the first one that cannot be taken ends the refill and the remaining slots stay idle until the next trip
+struct Source {
+    int fn;   // frame that moves in, -1: none
+    int row;  // stage row holding its channel values, -1: read them from global memory
+    uint32_t parity;
+};
+struct Planner {
+    unsigned int head, staged;
+    long long avail;
+    int taken;
+    bool blocked;
+};
+__device__ __forceinline__ Planner planner_init(const Ctrl *ctrl)
 {
-    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
-    const int nslots = W * T::LANES;
-    const bool mine = tid < nslots && ((fin >> tid) & 1u);  // one thread per stopping slot (all in warp 0)
-    const bool emit = !first && (p.bits || p.mc_mode != 0);
-    unsigned long long claim = 0;
-    bool was_over = false;
-    int old_it = 0;
-    if (mine) {
-        const int s = tid, w = s / T::LANES, lane = s % T::LANES;
-        was_over = (ctrl->gflag[buf][w] >> lane) & 1u;
-        old_it = (int)(trip - ctrl->start[s]);
-        if (!first)
-            p.iters[ctrl->fid[s]] = was_over ? -1 : (p.max_iter == 0 ? (int)((ctrl->fail[buf][w] >> lane) & 1u) : old_it);
-        // With claim_ahead the slot's next frame was taken from the queue (and its channel values pulled into L2)
-        // when the previous one moved in; the atomic issued here is for the frame after, and its round trip
-        // overlaps the passes below.
-        claim = atomicAdd(p.queue, 1ull);
-        const int f = p.claim_ahead ? ctrl->next[s] : queue_frame(p, claim, frames);
-        ctrl->newfid[s] = f;
-        if (p.mc_mode == 2 && f >= 0)
-            ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed, lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)f));
-        ctrl->errs[s] = 0u;
+    return Planner{ctrl->q_head, ctrl->q_staged, ctrl->avail, 0, false};
+}
+__device__ __forceinline__ Source planner_next(const KParams &p, const Ctrl *ctrl, Planner &pl, int s, bool sync)
+{
+    if (sync) return Source{ctrl->newfid[s], -1, 0u};
+    if (pl.blocked || pl.taken >= p.fifo_depth) { pl.blocked = true; return Source{-1, -1, 0u}; }
+    const unsigned int e = pl.head + (unsigned int)pl.taken;
+    const int f = ctrl->q_fid[e % (unsigned int)p.fifo_depth];
+    if (f < 0) { pl.blocked = true; return Source{-1, -1, 0u}; }
+    if (e < pl.staged) {
+        ++pl.taken;
+        return Source{f, (int)(e % (unsigned int)p.stage_rows), (e / (unsigned int)p.stage_rows) & 1u};
     }
-    __syncthreads();
-    if (p.mc_mode != 0 && emit) {
+    if (p.mc_mode == 0 && (long long)f >= pl.avail) { pl.blocked = true; return Source{-1, -1, 0u}; }
+    ++pl.taken;
+    return Source{f, -1, 0u};
+}
+
+// What a refill pass did, for the header update that follows it.
+struct Refill {
+    uint32_t taken;             // slots that received a frame
+    int ntake;                  // entries taken from the CTA's queue
+    unsigned long long claim;   // thread 0: first of the `ntake` queue positions claimed to replace them
+    bool drained;               // sync claims only: the queue is exhausted
+};
+
+template <class T>
+__device__ __noinline__ Refill refill_pass(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr, char *stage,
+                                              uint32_t want, uint32_t active, bool sync, int n, int E, int W,
+                                              long long frames, unsigned int trip, int buf)
+{
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int nslots = W * T::LANES;
+    const uint32_t report = want & active;  // slots whose frame leaves
+    const bool mine = tid < nslots && ((want >> tid) & 1u);  // one thread per slot (all in warp 0)
+    Refill out{0u, 0, 0ull, false};
+    if (mine && ((report >> tid) & 1u)) {
+        const int s = tid, w = s / T::LANES, lane = s % T::LANES;
+        const bool was_over = (ctrl->gflag[buf][w] >> lane) & 1u;
+        const int old_it = (int)(trip - 1u - ctrl->start[s]);  // decided at the end of trip - 1
+        p.iters[ctrl->fid[s]] = was_over ? -1 : (p.max_iter == 0 ? (int)((ctrl->fail[buf][w] >> lane) & 1u) : old_it);
+    }
+    if (sync) {
+        // first fill of the CTA, and every refill of a launch whose queue is too short to claim ahead
+        if (mine) {
+            const int s = tid;
+            const int f = queue_frame(p, atomicAdd(p.queue, 1ull), frames);
+            if (f >= 0 && p.avail)
+                while (frames_arrived(p, frames) <= (long long)f) __nanosleep(200);
+            ctrl->newfid[s] = f;
+        }
+        __syncthreads();
+    }
+    // ---- plan (identical in every thread)
+    {
+        Planner pl = planner_init(ctrl);
+        for (uint32_t left = want; left; left &= left - 1u) {
+            const int s = __ffs(left) - 1;
+            const Source src = planner_next(p, ctrl, pl, s, sync);
+            if (src.fn >= 0) out.taken |= 1u << s;
+            else if (sync) out.drained = true;
+            if (mine && s == tid) {
+                if (!sync) ctrl->newfid[s] = src.fn;
+                if (p.mc_mode == 2 && src.fn >= 0)
+                    ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed, lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)src.fn));
+            }
+        }
+        out.ntake = pl.taken;
+    }
+    // the positions that replace the entries taken: the atomic's round trip overlaps this pass and the variable phase
+    if (!sync && tid == 0 && out.ntake > 0) out.claim = atomicAdd(p.queue, (unsigned long long)out.ntake);
+
+    const bool emit = p.bits || p.mc_mode != 0;
+    if (p.mc_mode != 0) {
         // Monte-Carlo mode generates the channel values with another thread-to-variable mapping, so the decoded
         // bits (kept in the channel words) are collected first
-        for (uint32_t left = fin; left; left &= left - 1u) {
-            const int s = __ffs(left) - 1;
-            const int fo = ctrl->fid[s];
-            const uint32_t *lw = llr + (size_t)(s / T::LANES) * n;
-            if (fo >= 0)
+        if (emit && report) {
+            for (uint32_t left = report; left; left &= left - 1u) {
+                const int s = __ffs(left) - 1;
+                const int fo = ctrl->fid[s];
+                const uint32_t *lw = llr + (size_t)(s / T::LANES) * n;
                 for (int base = 0; base < n; base += nthreads) {
                     const int v = base + tid;
                     emit_word(p, ctrl, s, fo, v, n, v < n ? T::hd_bit(lw[v], s % T::LANES) : 0u);
                 }
+            }
         }
-        __syncthreads();
+        __syncthreads();  // (also orders the owners' lehmer[] stores before their use below)
     }
     uint32_t bad_slots = 0;
-    for (uint32_t left = fin; left; left &= left - 1u) {
+    Planner pl = planner_init(ctrl);
+    for (uint32_t left = want; left; left &= left - 1u) {
         const int s = __ffs(left) - 1;
         const int w = s / T::LANES, lane = s % T::LANES;
-        const int fo = emit ? ctrl->fid[s] : -1, fn = ctrl->newfid[s];
-        uint32_t *ew = edge + (size_t)w * E, *lw = llr + (size_t)w * n;
+        const Source src = planner_next(p, ctrl, pl, s, sync);
+        const int fn = src.fn;
+        uint32_t *lw = llr + (size_t)w * n;
         if (p.mc_mode == 0) {
-            uint32_t *bits_out = (fo >= 0 && p.bits) ? p.bits + (size_t)fo * p.nw32 : nullptr;
+            const int fo = (emit && ((report >> s) & 1u)) ? ctrl->fid[s] : -1;
+            uint32_t *bits_out = fo >= 0 ? p.bits + (size_t)fo * p.nw32 : nullptr;
+            if (fn < 0 && !bits_out) continue;
             bool bad;
-            if (p.llr_bits == 16)
+            if (fn >= 0 && src.row >= 0) {
+                // channel values staged in shared memory by cp.async.bulk; the copy started at the 16-byte line
+                // below the frame's first byte
+                mbar_wait(&ctrl->bar[src.row], src.parity);
+                const uintptr_t first = reinterpret_cast<uintptr_t>(p.llr) + (size_t)fn * n * 2u;
+                const int16_t *row = reinterpret_cast<const int16_t *>(stage + (size_t)src.row * p.stage_stride + (first & 15u));
+                bad = swap_frame<T>(lw, lane, bits_out, row, n);
+            } else if (p.llr_bits == 16) {
                 bad = swap_frame<T>(lw, lane, bits_out, fn >= 0 ? reinterpret_cast<const int16_t *>(p.llr) + (size_t)fn * n : nullptr, n);
-            else
+            } else {
                 bad = swap_frame<T>(lw, lane, bits_out, fn >= 0 ? reinterpret_cast<const int *>(p.llr) + (size_t)fn * n : nullptr, n);
+            }
             if (bad) bad_slots |= 1u << s;
+        } else if (fn < 0) {
+            continue;
         } else if (p.mc_mode == 1) {
             for (int q = tid; 4 * q < n; q += nthreads) {
-                float z[4] = {0.f, 0.f, 0.f, 0.f};
-                if (fn >= 0) philox_normals(p, p.mc_first + (unsigned long long)fn, (uint32_t)q, z);
+                float z[4];
+                philox_normals(p, p.mc_first + (unsigned long long)fn, (uint32_t)q, z);
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
                     const int v = 4 * q + h;
                     if (v < n) {
                         bool bad;
-                        const int val = fn >= 0 ? quantise_llr(p, (double)z[h], cw_bit(p, fn, v)) : 0;
-                        T::store_lane(&lw[v], lane, T::llr_lane(val, bad));
+                        T::store_lane(&lw[v], lane, T::llr_lane(quantise_llr(p, (double)z[h], cw_bit(p, fn, v)), bad));
                         if (bad) bad_slots |= 1u << s;
                     }
                 }
@@ -968,64 +1130,122 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
         } else {
             for (int v = tid; v < n; v += nthreads) {
                 bool bad;
-                const int val = fn >= 0 ? quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], p.mc_pow[v])), cw_bit(p, fn, v)) : 0;
+                const int val = quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], p.mc_pow[v])), cw_bit(p, fn, v));
                 T::store_lane(&lw[v], lane, T::llr_lane(val, bad));
                 if (bad) bad_slots |= 1u << s;
             }
         }
-        // its messages start from zero
-        if (!first)
-            for (int i = tid; i < E; i += nthreads) T::store_lane(&ew[i], lane, 0u);
     }
-    for (int s = 0; bad_slots; ++s, bad_slots >>= 1)  // judged by the coming trip's stop decision
-        if (bad_slots & 1u) atomicOr(&ctrl->gflag[buf == 2 ? 0 : buf + 1][s / T::LANES], 1u << (s % T::LANES));
-    if (p.mc_mode != 0 && p.mc_pin_count > 0) {  // shortening: known positions pinned (PerfTest.cpp:410-414)
+    if (p.mc_mode != 0 && p.mc_pin_count > 0 && out.taken) {  // shortening: known positions pinned (PerfTest.cpp:410-414)
         __syncthreads();
         for (int i = tid; i < p.mc_pin_count; i += nthreads) {
             const int v = p.mc_pin[i];
-            for (uint32_t left = fin; left; left &= left - 1u) {
+            for (uint32_t left = out.taken; left; left &= left - 1u) {
                 const int s = __ffs(left) - 1;
-                if (ctrl->newfid[s] < 0) continue;
                 bool bad;
                 T::store_lane(&llr[(size_t)(s / T::LANES) * n + v], s % T::LANES, T::llr_lane(p.mc_pin_value, bad));
+                if (bad) bad_slots |= 1u << s;
             }
         }
     }
+    for (int s = 0; bad_slots; ++s, bad_slots >>= 1)  // judged by the coming trip's stop decision
+        if (bad_slots & 1u) atomicOr(&ctrl->gflag[buf == 2 ? 0 : buf + 1][s / T::LANES], 1u << (s % T::LANES));
+    (void)edge; (void)E;
     __syncthreads();
-    int ahead = -1;
-    if (mine) {
+    return out;
+}
+
+// After a refill pass, between the barrier that ends the variable phase and the check phase (parity-mode launches:
+// before the variable phase, behind a barrier of its own): nothing here is read by the check phase, and everything
+// is read by all threads only after the barrier that ends it.
+//   slot owners  Monte-Carlo counters and completion signalling of the frames that left, new slot headers
+//   thread 0     the CTA's queue of claimed frames: entries that replace the ones taken, bulk copies of the channel
+//                values of the first `stage_rows` entries into their stage rows, the fed launch's arrival mark
+//   warp 0       L2 prefetch of the channel values the refill will read from global memory
+template <class T>
+__device__ __noinline__ void header_update(const KParams &p, Ctrl *ctrl, char *stage, uint32_t want, uint32_t active_before,
+                                              const Refill &rf, bool sync, int n, int W, long long frames, unsigned int trip, int rbuf)
+{
+    const int tid = threadIdx.x, lane_id = tid & 31;
+    const int nslots = W * T::LANES;
+    const uint32_t report = want & active_before;
+    if (tid < nslots && ((want >> tid) & 1u)) {
         const int s = tid;
-        if (!first && p.mc_mode != 0 && !was_over) {  // flagged frames are counted by their exact re-decode
-            const unsigned int e = ctrl->errs[s];
-            if (p.mc_frame_err) p.mc_frame_err[ctrl->fid[s]] = (unsigned short)min(e, 65535u);
-            atomicAdd(&p.mc_counters[0], 1ull);
-            if (e) atomicAdd(&p.mc_counters[1], 1ull);
-            if (e) atomicAdd(&p.mc_counters[2], (unsigned long long)e);
-            atomicAdd(&p.mc_counters[3], (unsigned long long)old_it);
+        if ((report >> s) & 1u) {
+            const int w = s / T::LANES, lane = s % T::LANES;
+            const bool was_over = (ctrl->gflag[rbuf][w] >> lane) & 1u;
+            const int fo = ctrl->fid[s];
+            if (p.mc_mode != 0 && !was_over) {  // flagged frames are counted by their exact re-decode
+                const unsigned int e = ctrl->errs[s];
+                if (p.mc_frame_err) p.mc_frame_err[fo] = (unsigned short)min(e, 65535u);
+                atomicAdd(&p.mc_counters[0], 1ull);
+                if (e) atomicAdd(&p.mc_counters[1], 1ull);
+                if (e) atomicAdd(&p.mc_counters[2], (unsigned long long)e);
+                atomicAdd(&p.mc_counters[3], (unsigned long long)(trip - 1u - ctrl->start[s]));
+            }
+            if (p.done_count) {
+                // results of frame fo (iteration count by this thread, bits by the ballot leaders before the barriers
+                // behind us) are complete: count it, and tell the host when its chunk is
+                const int chunk = fo / p.done_chunk;
+                const long long lo = (long long)chunk * p.done_chunk;
+                const unsigned int size = (unsigned int)min((long long)p.done_chunk, frames - lo);
+                __threadfence();
+                if (atomicAdd(&p.done_count[chunk], 1u) + 1u == size) {
+                    __threadfence_system();
+                    p.done_flag[chunk] = 1u;
+                }
+            }
         }
-        ctrl->fid[s] = ctrl->newfid[s];
-        ctrl->start[s] = trip + 1u;  // its first (initialising) variable phase runs in the coming trip
-        if (p.claim_ahead) {
-            ahead = queue_frame(p, claim, frames);
-            ctrl->next[s] = ahead;
-        }
+        ctrl->errs[s] = 0u;
+        ctrl->fid[s] = ((rf.taken >> s) & 1u) ? ctrl->newfid[s] : -1;
+        ctrl->start[s] = trip;  // its first (initialising) variable phase runs in this trip
     }
-    if (p.claim_ahead && p.mc_mode == 0 && tid < 32) {
-        // pull the channel values of the frames just claimed into L2: they are read one frame time from now
+    if (sync && !p.claim_ahead) return;
+    if (tid == 0) {
+        const unsigned int L = (unsigned int)p.fifo_depth, S = (unsigned int)p.stage_rows;
+        unsigned int head = ctrl->q_head;
+        if (sync) {
+            // first trip of a launch that claims ahead: fill the queue (the slots took their frames before it)
+            const unsigned long long base = atomicAdd(p.queue, (unsigned long long)L);
+            for (unsigned int k = 0; k < L; ++k) ctrl->q_fid[k] = queue_frame(p, base + k, frames);
+        } else {
+            for (int k = 0; k < rf.ntake; ++k)
+                ctrl->q_fid[(head + L + (unsigned int)k) % L] = queue_frame(p, rf.claim + (unsigned long long)k, frames);
+            head += (unsigned int)rf.ntake;
+            ctrl->q_head = head;
+        }
+        const long long avail = frames_arrived(p, frames);
+        ctrl->avail = avail;
+        unsigned int staged = max(ctrl->q_staged, head);
+        if (S > 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the rows were read through the generic proxy
+            const size_t bytes = (size_t)n * 2u;
+            for (; staged < head + S; ++staged) {
+                const int f = ctrl->q_fid[staged % L];
+                if (f < 0 || (long long)f >= avail) break;
+                const uintptr_t first = reinterpret_cast<uintptr_t>(p.llr) + (size_t)f * bytes;
+                const uintptr_t lo = first & ~(uintptr_t)15u;
+                const uint32_t len = (uint32_t)(((first + bytes + 15u) & ~(uintptr_t)15u) - lo);
+                unsigned long long *bar = &ctrl->bar[staged % S];
+                mbar_expect_tx(bar, len);
+                bulk_copy_g2s(stage + (size_t)(staged % S) * p.stage_stride, reinterpret_cast<const void *>(lo), len, bar);
+            }
+        }
+        ctrl->q_staged = staged;
+    }
+    if (!sync && p.mc_mode == 0 && tid < 32 && rf.ntake > 0 && p.stage_rows < p.fifo_depth) {
+        // entries that will not be staged: pull their channel values into L2, they are read a frame time from now
+        const unsigned long long claim = __shfl_sync(0xffffffffu, rf.claim, 0);
         const size_t bytes = (size_t)n * (p.llr_bits >> 3);
-        for (uint32_t left = fin; left; left &= left - 1u) {
-            const int f = __shfl_sync(0xffffffffu, ahead, __ffs(left) - 1);
-            if (f >= 0) {
+        for (int k = 0; k < rf.ntake; ++k) {
+            const int f = queue_frame(p, claim + (unsigned long long)k, frames);
+            if (f >= 0 && !p.avail) {
                 const char *first_byte = reinterpret_cast<const char *>(p.llr) + (size_t)f * bytes;
                 const char *line = first_byte - (reinterpret_cast<uintptr_t>(first_byte) & 127u) + (size_t)lane_id * 128u;
                 for (; line < first_byte + bytes; line += 32 * 128) prefetch_l2(line);
             }
         }
     }
-    __syncthreads();
-    int active = 0;
-    for (int s = 0; s < nslots; ++s) active += ctrl->fid[s] >= 0;
-    return active;
 }
 
 // Stop / continue decision of every slot, taken after the check phase (its votes are the syndrome of the state the
@@ -1033,18 +1253,24 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
 // MAX_ITER (:63), decode_fixpoint's pre-check on the channel hard decisions (:443-450, iteration count 0), the
 // hard-decision-only mode (max_iter == 0) and lanes that left the packed range.  Every warp evaluates all slots
 // (lane = slot) from words nobody writes before the next barrier, so the mask of stopping slots is the same in
-// every thread and no barrier is needed to agree on it.
+// every thread and no barrier is needed to agree on it.  Idle slots ask for a frame while the CTA's queue of
+// claimed frames has one.
 template <class T>
-__device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, int W, unsigned int trip, int buf)
+__device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, int W, uint32_t active, bool fifo,
+                                                  unsigned int trip, int buf)
 {
     const int s = threadIdx.x & 31;
     bool stop = false;
-    if (s < W * T::LANES && ctrl->fid[s] >= 0) {
-        const int w = s / T::LANES, lane = s % T::LANES;
-        const int it = (int)(trip - ctrl->start[s]);  // 0: the frame has only been initialised
-        const bool pass = !((ctrl->fail[buf][w] >> lane) & 1u);
-        const bool over = (ctrl->gflag[buf][w] >> lane) & 1u;
-        stop = it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over;
+    if (s < W * T::LANES) {
+        if ((active >> s) & 1u) {
+            const int w = s / T::LANES, lane = s % T::LANES;
+            const int it = (int)(trip - ctrl->start[s]);  // 0: the frame has only been initialised
+            const bool pass = !((ctrl->fail[buf][w] >> lane) & 1u);
+            const bool over = (ctrl->gflag[buf][w] >> lane) & 1u;
+            stop = it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over;
+        } else if (fifo) {
+            stop = ctrl->q_fid[ctrl->q_head % (unsigned int)p.fifo_depth] >= 0;
+        }
     }
     const uint32_t fin = __ballot_sync(0xffffffffu, stop);
     // the buffer the trip after next votes into (last read one decision ago, before two barriers)
@@ -1087,22 +1313,31 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
     const int n = N ? N : p.n, m = M ? M : p.m, E = EA ? EA : (M ? DC * M : p.E), W = p.W;
     uint32_t *edge = smem;                 // [W][E]
     uint32_t *llr = edge + (size_t)W * E;  // [W][n] channel values (+ the hard decision of the last posterior)
-    Ctrl *ctrl = reinterpret_cast<Ctrl *>(llr + (size_t)W * n);
+    Ctrl *ctrl = reinterpret_cast<Ctrl *>((reinterpret_cast<uintptr_t>(llr + (size_t)W * n) + 15u) & ~(uintptr_t)15u);
     // degree tables next to the control block (irregular codes dispatch on them once per node and phase)
     constexpr bool REGV = PREFETCH_VEDGE && M != 0 && REG && DV <= 8 && ARRP == 0;
     uint8_t *cdeg_s = reinterpret_cast<uint8_t *>(ctrl + 1);
     uint8_t *vdeg_s = cdeg_s + (REG ? 0 : ((m + 15) & ~15));
+    uint8_t *tables_end = vdeg_s + ((REGV || ARRP) ? 0 : ((n + 15) & ~15));
+    // stage rows: 16-byte aligned, after the tables
+    char *stage = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(tables_end) + 15u) & ~(uintptr_t)15u);
     if (!REG) for (int i = tid; i < m; i += nthreads) cdeg_s[i] = p.cdeg[i];
     if (!REGV && !ARRP) for (int i = tid; i < n; i += nthreads) vdeg_s[i] = p.vdeg[i];
     const int nslots = W * T::LANES;
     const long long frames = p.count ? (long long)*p.count : p.frames;
+    const bool parity_out = p.post || p.v2c;
 
     for (int i = tid; i < W * (E + n); i += nthreads) smem[i] = 0u;
     if (tid < MAX_W)
         for (int b = 0; b < 3; ++b) { ctrl->fail[b][tid] = 0u; ctrl->gflag[b][tid] = 0u; }
     if (tid < MAX_SLOTS) {
-        ctrl->fid[tid] = -1; ctrl->start[tid] = 0u; ctrl->newfid[tid] = -1;
-        ctrl->next[tid] = (p.claim_ahead && tid < nslots) ? queue_frame(p, atomicAdd(p.queue, 1ull), frames) : -1;
+        ctrl->fid[tid] = -1; ctrl->start[tid] = 0u; ctrl->newfid[tid] = -1; ctrl->errs[tid] = 0u; ctrl->lehmer[tid] = 0u;
+    }
+    if (tid < MAX_FIFO) ctrl->q_fid[tid] = -1;
+    if (tid == 0) {
+        ctrl->q_head = 0u; ctrl->q_staged = 0u; ctrl->avail = 0;
+        for (int r = 0; r < MAX_STAGE; ++r) mbar_init(&ctrl->bar[r], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
@@ -1114,29 +1349,58 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
 #define LDPC_MARK(k) do { } while (0)
 #endif
 
-    uint32_t fin = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);  // slots to (re)fill
-    bool first = true;
+    const uint32_t all_slots = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);
+    uint32_t want = all_slots;  // slots to serve at the top of the trip: stopped frames, idle slots
+    uint32_t active = 0u;       // slots that hold a frame
+    bool sync = true;           // the first fill claims per slot; later refills take the frames claimed ahead
+    bool drained = false;       // sync claims: the queue is exhausted
     // trip t votes into buffer t % 3; `buf` is the buffer of the trip that ended last (what a refill reports from)
     unsigned int trip = 0;
     int buf = 2;
     for (;;) {
-        if (fin) {
-            // trip - 1 is the trip whose stop decision released the slots
-            const int active = finish_and_refill<T>(p, ctrl, edge, llr, fin, first, n, E, W, frames, trip - 1u, buf);
-            if (active == 0) break;
-            first = false;
+        Refill rf{0u, 0, 0ull, false};
+        const uint32_t before = active;
+        const uint32_t served = want;
+        const bool served_sync = sync;
+        if (served) {
+            rf = refill_pass<T>(p, ctrl, edge, llr, stage, served, before, sync, n, E, W, frames, trip, buf);
+            active = (active & ~served) | rf.taken;
+            drained |= rf.drained;
+        }
+        const int rbuf = buf;
+        if (!active) {
+            // nothing to decode right now: finish the bookkeeping, then either leave or (fed launch whose next
+            // frames have not arrived yet) look again
+            if (served || p.claim_ahead) header_update<T>(p, ctrl, stage, served, before, rf, served_sync, n, W, frames, trip, rbuf);
+            __syncthreads();
+            const bool more = p.claim_ahead ? ctrl->q_fid[ctrl->q_head % (unsigned int)p.fifo_depth] >= 0 : !drained;
+            if (!more) break;
+            __syncthreads();  // q_* were read above; thread 0 rewrites them in the next header update
+            __nanosleep(500);
+            want = all_slots;
+            sync = !p.claim_ahead;
+            continue;
         }
         buf = buf == 2 ? 0 : buf + 1;
         LDPC_MARK(0);
-        if (p.post || p.v2c) variable_phase_parity<T, DV, REGV, ARRP>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s);
-        else if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), false>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E);
-        else variable_phase<T, DV, false, REGV>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s);
+        if (parity_out) {
+            if (served) {
+                header_update<T>(p, ctrl, stage, served, before, rf, served_sync, n, W, frames, trip, rbuf);
+                __syncthreads();
+            }
+            variable_phase_parity<T, DV, REGV, ARRP>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s, rf.taken);
+        } else {
+            variable_phase_fast<T, DV, REGV, ARRP>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s, rf.taken);
+        }
         __syncthreads();
         LDPC_MARK(1);
+        if (served && !parity_out) header_update<T>(p, ctrl, stage, served, before, rf, served_sync, n, W, frames, trip, rbuf);
         check_phase<T, DC, REG, NI>(p, ctrl->fail[buf], edge, cdeg_s, items, m, E, W);
         __syncthreads();
         LDPC_MARK(2);
-        fin = stop_decision<T>(p, ctrl, W, trip, buf);
+        sync = !p.claim_ahead;
+        want = stop_decision<T>(p, ctrl, W, active, !sync, trip, buf);
+        if (sync && !drained) want |= all_slots & ~active;  // short queue: idle slots claim for themselves
         ++trip;
         LDPC_MARK(3);
     }

@@ -144,6 +144,7 @@ typedef struct {
     int grid;                  /* CTAs per launch                                             */
     int smem_bytes;            /* dynamic shared memory per CTA (packed kernel)               */
     int smem_bytes32;
+    int stage_rows;            /* rows of shared memory the last launch filled by TMA bulk copies (0: none) */
 } ldpc_decoder_stats;
 
 int ldpc_decoder_get_stats(const ldpc_decoder *dec, ldpc_decoder_stats *out);

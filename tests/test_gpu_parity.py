@@ -302,7 +302,7 @@ def test_int16_host_entry_equals_int32_host_entry(fp, po, name):
     t = tables_of(code)
     rate = fp.codes.INFO_BITS[name] / code.n
     llr = channel_frames(code.n, rate, 2.0 if name == "wifi" else 4.0, 9000, seed=99)
-    llr[7] *= 9          # leaves the 13-bit guard range but fits int16: exact int32 re-decode from the int16 input
+    llr[7] *= 40         # leaves the 13-bit guard range (clipped to int16): exact int32 re-decode from the int16 input
     llr = np.clip(llr, -32768, 32767)
     dec = fp.Decoder(code, precheck=(name == "a5"))
     a = dec.decode(llr, want_post=True)
