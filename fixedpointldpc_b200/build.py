@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libldpc_b200.so")
-SOURCES = ["ldpc_decoder.cu", "ldpc_encode.cu", "ldpc_code.cpp"]
+SOURCES = ["ldpc_decoder.cu", "ldpc_encode.cu", "ldpc_multi.cu", "ldpc_code.cpp"]
 HEADERS = ["ldpc_kernels.cuh", "ldpc_code.hpp", os.path.join("..", "..", "include", "ldpc_capi.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -62,8 +62,9 @@ def build(force=False, verbose=False):
 def build_lib(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
+    # NCCL is bound at run time (dlopen in ldpc_multi.cu); only its header is needed here
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, f) for f in SOURCES]
+          [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl", "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

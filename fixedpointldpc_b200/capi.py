@@ -23,6 +23,8 @@ EXPORTS = (
     "ldpc_decoder_cfg_default", "ldpc_decoder_create", "ldpc_decoder_destroy", "ldpc_decode_batch", "ldpc_decode_batch_i16",
     "ldpc_decode_batch_device", "ldpc_decoder_sync", "ldpc_decoder_get_stats", "ldpc_device_count",
     "ldpc_mc_run", "ldpc_mc_run_device", "ldpc_mc_channel", "ldpc_hard_decision_batch",
+    "ldpc_decoder_device", "ldpc_mc_group_create", "ldpc_mc_group_size", "ldpc_mc_group_run", "ldpc_mc_group_destroy",
+    "ldpc_mc_run_multi",
     "ldpc_encode_batch", "ldpc_encode_batch_device", "ldpc_gen_load", "ldpc_gen_from_code", "ldpc_gen_save", "ldpc_gen_free", "ldpc_gen_dims", "ldpc_gen_indices", "ldpc_gen_encode",
 )
 STREAM_PHILOX, STREAM_REFERENCE = 1, 2
@@ -56,6 +58,17 @@ class McCfg(C.Structure):
 class McCounters(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("frame_errors", C.c_uint64), ("bit_errors", C.c_uint64),
                 ("iter_sum", C.c_uint64)]
+
+
+class McStop(C.Structure):
+    _fields_ = [("target_block_errors", C.c_uint64), ("max_frames", C.c_uint64), ("frames_per_round", C.c_size_t),
+                ("count_iterations", C.c_int), ("iters_out", C.c_void_p), ("iters_cap", C.c_size_t)]
+
+
+class McResult(C.Structure):
+    _fields_ = [("frames", C.c_uint64), ("block_errors", C.c_uint64), ("errors", C.c_uint64), ("iter_sum", C.c_uint64),
+                ("iter_hist", C.c_uint64 * 32), ("rounds", C.c_uint64), ("reached", C.c_int), ("devices", C.c_int),
+                ("seconds", C.c_double)]
 
 
 _lib = None
@@ -99,6 +112,13 @@ def load_library():
     L.ldpc_mc_run.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp, vp, C.POINTER(McCounters)]
     L.ldpc_mc_run_device.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp, vp, vp, vp]
     L.ldpc_mc_channel.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp]
+    L.ldpc_decoder_device.argtypes = [vp]
+    L.ldpc_mc_group_create.restype = vp
+    L.ldpc_mc_group_create.argtypes = [C.POINTER(vp), C.c_int, ip]
+    L.ldpc_mc_group_size.argtypes = [vp]
+    L.ldpc_mc_group_run.argtypes = [vp, C.POINTER(McCfg), C.POINTER(McStop), C.POINTER(McResult)]
+    L.ldpc_mc_group_destroy.argtypes = [vp]
+    L.ldpc_mc_run_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(McCfg), C.POINTER(McStop), C.POINTER(McResult)]
     L.ldpc_hard_decision_batch.argtypes = [vp, vp, C.c_size_t, vp, vp]
     L.ldpc_gen_load.restype = vp
     L.ldpc_gen_load.argtypes = [C.c_char_p, ip]
@@ -364,6 +384,48 @@ class Decoder:
     def close(self):
         if self._h:
             load_library().ldpc_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class McGroup:
+    """One Monte-Carlo point on several GPUs of the box (ldpc_mc_group_*): one Decoder per device, one host thread per
+    device inside the library, counters all-reduced over NCCL once per round."""
+
+    def __init__(self, decoders):
+        L = load_library()
+        self.decoders = list(decoders)
+        arr = (C.c_void_p * len(self.decoders))(*[d._h for d in self.decoders])
+        err = C.c_int()
+        self._h = L.ldpc_mc_group_create(arr, len(self.decoders), C.byref(err))
+        if not self._h:
+            _check(err.value)
+
+    def run(self, snr, target_block_errors=100, max_frames=0, frames_per_round=0, count_iterations=False, want_iters=0, **kw):
+        """Returns dict(frames, block_errors, errors, iter_sum, iter_hist, rounds, reached, devices, seconds[, iters])."""
+        cfg, keep = self.decoders[0]._mc_cfg(snr, **kw)
+        stop = McStop(target_block_errors, max_frames, frames_per_round, int(count_iterations), None, 0)
+        log = None
+        if want_iters:
+            log = np.full(want_iters, -2, np.int32)
+            stop.iters_out, stop.iters_cap = log.ctypes.data, want_iters
+        res = McResult()
+        _check(load_library().ldpc_mc_group_run(self._h, C.byref(cfg), C.byref(stop), C.byref(res)))
+        del keep
+        out = {k: getattr(res, k) for k in ("frames", "block_errors", "errors", "iter_sum", "rounds", "reached", "devices", "seconds")}
+        out["iter_hist"] = np.array(list(res.iter_hist), np.int64)
+        if log is not None:
+            out["iters"] = log[:min(want_iters, out["frames"])]
+        return out
+
+    def close(self):
+        if self._h:
+            load_library().ldpc_mc_group_destroy(self._h)
             self._h = None
 
     def __del__(self):

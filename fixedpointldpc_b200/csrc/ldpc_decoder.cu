@@ -144,6 +144,11 @@ struct ldpc_decoder {
     int *d_fb_index = nullptr, *d_fb_count = nullptr;
     unsigned long long *d_fb_total = nullptr;
     size_t fb_cap = 0;
+    // fed launches of the host pipeline: arrival mark, per-chunk completion counters, host-mapped completion flags
+    unsigned long long *d_feed_avail = nullptr, *h_feed_marks = nullptr;
+    unsigned int *d_done_count = nullptr, *h_done_flag = nullptr, *d_done_flag = nullptr;
+    size_t feed_chunks_cap = 0, feed_marks_cap = 0;
+    cudaEvent_t ev_feed = nullptr;
     // Monte-Carlo mode resources
     uint32_t *d_mc_pow = nullptr;      // a^(v+1) mod m
     uint32_t mc_jump = 0;              // a^n mod m
@@ -350,6 +355,7 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     p.stage_rows = 0;
     if (p.claim_ahead && !mc && llr_bits == 16 && !getenv("LDPC_NO_STAGE"))
         p.stage_rows = std::max(0, std::min({(pl.smem_limit - pl.smem) / p.stage_stride, (int)MAX_STAGE, p.fifo_depth}));
+    p.tables_bytes = (pl.kernel.cdeg_in_smem ? ((c.m + 15) & ~15) : 0) + (pl.kernel.vdeg_in_smem ? ((c.n + 15) & ~15) : 0);
     const int smem = pl.smem + p.stage_rows * p.stage_stride;
     CUDA_TRY(cudaMemsetAsync(p.queue, 0, sizeof(unsigned long long), st));
     pl.kernel.fn<<<grid, pl.threads, smem, st>>>(p);
@@ -373,7 +379,8 @@ static int ensure_fallback_list(ldpc_decoder &d, size_t frames)
 }
 
 static int decode_device(ldpc_decoder &d, const void *llr, int llr_bits, long long frames, int *iters,
-                         uint32_t *bits, int *post, int *v2c, cudaStream_t st, const KParams *mc = nullptr)
+                         uint32_t *bits, int *post, int *v2c, cudaStream_t st, const KParams *mc = nullptr,
+                         const Feed *fed = nullptr)
 {
     if (!mc && llr_bits != 16 && llr_bits != 32) { set_error("llr_bits must be 16 or 32"); return LDPC_ERR_ARG; }
     if (frames > 0x7fffffffLL) { set_error("more than 2^31-1 frames in one call"); return LDPC_ERR_ARG; }
@@ -383,8 +390,8 @@ static int decode_device(ldpc_decoder &d, const void *llr, int llr_bits, long lo
     // short rows read as zero like the reference's untouched EdgeRAM words
     if (v2c) CUDA_TRY(cudaMemsetAsync(v2c, 0, (size_t)frames * d.code.dc_max * d.code.m * sizeof(int), st));
     if (d.cfg.precision == 32)
-        return launch(d, d.plan32, 1, llr, llr_bits, frames, iters, bits, post, v2c, nullptr, nullptr, st, mc);
-    int rc = launch(d, d.plan16, 0, llr, llr_bits, frames, iters, bits, post, v2c, nullptr, nullptr, st, mc);
+        return launch(d, d.plan32, 1, llr, llr_bits, frames, iters, bits, post, v2c, nullptr, nullptr, st, mc, fed);
+    int rc = launch(d, d.plan16, 0, llr, llr_bits, frames, iters, bits, post, v2c, nullptr, nullptr, st, mc, fed);
     if (rc != LDPC_OK || d.cfg.precision == 16) return rc;
     // Exact int32 re-decode of the flagged frames, in place and without a host round trip: the
     // second launch reads the frame list and its length from device memory.
@@ -733,6 +740,10 @@ void ldpc_decoder_destroy(ldpc_decoder *d)
     cudaFree(d->d_cdeg); cudaFree(d->d_vdeg); cudaFree(d->d_vedge); cudaFree(d->d_eorig);
     cudaFree(d->plan16.d_vorder); cudaFree(d->plan16.d_corder); cudaFree(d->plan32.d_vorder); cudaFree(d->plan32.d_corder); cudaFree(d->d_queue);
     cudaFree(d->d_fb_index); cudaFree(d->d_fb_count); cudaFree(d->d_fb_total);
+    cudaFree(d->d_feed_avail); cudaFree(d->d_done_count);
+    if (d->h_feed_marks) cudaFreeHost(d->h_feed_marks);
+    if (d->h_done_flag) cudaFreeHost(d->h_done_flag);
+    if (d->ev_feed) cudaEventDestroy(d->ev_feed);
     cudaFree(d->d_mc_pow); cudaFree(d->d_mc_cw); cudaFree(d->d_mc_info); cudaFree(d->d_mc_pin);
     cudaFree(d->d_mc_iters); cudaFree(d->d_mc_ferr); cudaFree(d->d_mc_counters); cudaFree(d->d_mc_llr);
     if (d->stream) cudaStreamDestroy(d->stream);
@@ -747,6 +758,121 @@ int ldpc_decode_batch_device(ldpc_decoder *d, const void *d_llr, int llr_bits, s
     return ldpc::decode_device(*d, d_llr, llr_bits, (long long)frames, d_iters, d_bits, d_post, d_v2c, st);
 }
 
+// Host pipeline for long batches: ONE persistent decode launch per (up to 2^18-frame) batch.  The kernel starts at
+// once; the channel values follow in growing chunks on the copy-in stream, each chunk followed by an 8-byte copy
+// that moves the arrival mark the kernel polls (ldpc_kernels.cuh: KParams::avail); finished frames are counted per
+// result chunk on the device, the thread that completes a chunk raises a flag in host-mapped memory, and this
+// thread then copies that chunk's results out on the copy-out stream while the kernel decodes on.  No launch tails
+// between chunks, no idle slots while a chunk drains.
+static int decode_host_fed(ldpc_decoder *d, const char *llr, int llr_bits, size_t frames, int32_t *iters, uint32_t *bits)
+{
+    const ldpc_code &c = d->code;
+    const size_t esz = (size_t)llr_bits / 8, nw32 = (c.n + 31) / 32;
+    const size_t slots = (size_t)d->sm_count * d->plan16.kernel.ctas_per_sm * d->plan16.W * 2;
+    const size_t done_chunk = 8192;
+    int rc = ldpc::ensure_staging(*d, frames, false, false);
+    if (rc != LDPC_OK) return rc;
+    const size_t nchunks = (frames + done_chunk - 1) / done_chunk;
+    // copy-in chunks: one frame per slot first (the decode starts after a short copy), then doubling
+    std::vector<size_t> marks;
+    for (size_t at = 0, sz = std::max<size_t>(slots, 1024); at < frames; sz = std::min<size_t>(sz * 2, 1 << 15)) {
+        at = std::min(frames, at + sz);
+        marks.push_back(at);
+    }
+    if (!d->d_feed_avail) {
+        CUDA_TRY(cudaMalloc(&d->d_feed_avail, sizeof(unsigned long long)));
+        CUDA_TRY(cudaEventCreateWithFlags(&d->ev_feed, cudaEventDisableTiming));
+    }
+    if (d->feed_chunks_cap < nchunks) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(d->d_done_count); d->d_done_count = nullptr;
+        if (d->h_done_flag) cudaFreeHost(d->h_done_flag);
+        d->h_done_flag = nullptr; d->feed_chunks_cap = 0;
+        CUDA_TRY(cudaMalloc(&d->d_done_count, nchunks * sizeof(unsigned int)));
+        CUDA_TRY(cudaHostAlloc(&d->h_done_flag, nchunks * sizeof(unsigned int), cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer(&d->d_done_flag, d->h_done_flag, 0));
+        d->feed_chunks_cap = nchunks;
+    }
+    if (d->feed_marks_cap < marks.size()) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (d->h_feed_marks) cudaFreeHost(d->h_feed_marks);
+        d->h_feed_marks = nullptr; d->feed_marks_cap = 0;
+        CUDA_TRY(cudaHostAlloc(&d->h_feed_marks, marks.size() * sizeof(unsigned long long), cudaHostAllocDefault));
+        d->feed_marks_cap = marks.size();
+    }
+    for (size_t i = 0; i < marks.size(); ++i) d->h_feed_marks[i] = marks[i];
+    volatile unsigned int *flags = d->h_done_flag;
+    for (size_t i = 0; i < nchunks; ++i) flags[i] = 0u;
+    cudaStream_t sk = d->stream;
+    CUDA_TRY(cudaMemsetAsync(d->d_feed_avail, 0, sizeof(unsigned long long), sk));
+    CUDA_TRY(cudaMemsetAsync(d->d_done_count, 0, nchunks * sizeof(unsigned int), sk));
+    CUDA_TRY(cudaEventRecord(d->ev_feed, sk));
+    ldpc::Feed fed{d->d_feed_avail, d->d_done_count, d->d_done_flag, (int)done_chunk};
+    const int saved_precision = d->cfg.precision;
+    if (d->cfg.precision == 0) d->cfg.precision = 16;  // the re-decode of flagged frames follows below, after the fed launch
+    rc = ldpc::decode_device(*d, d->d_llr[0], llr_bits, (long long)frames, d->d_iters[0], bits ? d->d_bits[0] : nullptr,
+                             nullptr, nullptr, sk, nullptr, &fed);
+    d->cfg.precision = saved_precision;
+    if (rc != LDPC_OK) return rc;
+    // the channel values follow the launch
+    CUDA_TRY(cudaStreamWaitEvent(d->s_in, d->ev_feed, 0));
+    size_t at = 0;
+    cudaError_t e = cudaSuccess;
+    for (size_t i = 0; i < marks.size() && e == cudaSuccess; ++i) {
+        e = cudaMemcpyAsync((char *)d->d_llr[0] + at * c.n * esz, llr + at * c.n * esz, (marks[i] - at) * c.n * esz,
+                            cudaMemcpyHostToDevice, d->s_in);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(d->d_feed_avail, &d->h_feed_marks[i], sizeof(unsigned long long), cudaMemcpyHostToDevice, d->s_in);
+        at = marks[i];
+    }
+    if (e != cudaSuccess) {
+        // let the kernel run out instead of waiting for frames that will not come
+        unsigned long long all = frames;
+        cudaMemcpy(d->d_feed_avail, &all, sizeof all, cudaMemcpyHostToDevice);
+        cudaStreamSynchronize(sk);
+        ldpc::set_error(std::string("host pipeline copy-in: ") + cudaGetErrorString(e));
+        return LDPC_ERR_CUDA;
+    }
+    // results leave chunk by chunk as the kernel announces them
+    bool kernel_done = false;
+    for (size_t ch = 0; ch < nchunks; ++ch) {
+        for (unsigned spins = 0; !flags[ch] && !kernel_done; ++spins) {
+            if ((spins & 1023u) == 1023u) {
+                cudaError_t q = cudaStreamQuery(sk);
+                if (q == cudaSuccess) kernel_done = true;
+                else if (q != cudaErrorNotReady) { ldpc::set_error(std::string("decode kernel: ") + cudaGetErrorString(q)); return LDPC_ERR_CUDA; }
+            }
+        }
+        const size_t lo = ch * done_chunk, cnt = std::min(done_chunk, frames - lo);
+        CUDA_TRY(cudaMemcpyAsync(iters + lo, d->d_iters[0] + lo, cnt * sizeof(int), cudaMemcpyDeviceToHost, d->s_out));
+        if (bits) CUDA_TRY(cudaMemcpyAsync(bits + lo * nw32, d->d_bits[0] + lo * nw32, cnt * nw32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->s_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(sk));
+    if (saved_precision == 0) {
+        // exact int32 re-decode of the frames the packed kernel flagged (none on channel-generated frames): an
+        // ordinary launch over the device copy of the batch; its results replace the flagged ones
+        CUDA_TRY(cudaMemsetAsync(d->d_fb_count, 0, sizeof(int), sk));
+        ldpc::collect_flagged<<<(unsigned)((frames + 255) / 256), 256, 0, sk>>>(d->d_iters[0], (long long)frames, d->d_fb_index,
+                                                                                  d->d_fb_count, d->d_fb_total);
+        CUDA_TRY(cudaGetLastError());
+        d->stats.kernel_launches++;
+        int flagged = 0;
+        CUDA_TRY(cudaMemcpyAsync(&flagged, d->d_fb_count, sizeof(int), cudaMemcpyDeviceToHost, sk));
+        CUDA_TRY(cudaStreamSynchronize(sk));
+        if (flagged > 0) {
+            rc = ldpc::launch(*d, d->plan32, 1, d->d_llr[0], llr_bits, (long long)frames, d->d_iters[0], bits ? d->d_bits[0] : nullptr,
+                              nullptr, nullptr, d->d_fb_index, d->d_fb_count, sk);
+            if (rc != LDPC_OK) return rc;
+            CUDA_TRY(cudaStreamSynchronize(d->s_out));
+            CUDA_TRY(cudaMemcpyAsync(iters, d->d_iters[0], frames * sizeof(int), cudaMemcpyDeviceToHost, sk));
+            if (bits) CUDA_TRY(cudaMemcpyAsync(bits, d->d_bits[0], frames * nw32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sk));
+            CUDA_TRY(cudaStreamSynchronize(sk));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(d->s_out));
+    return LDPC_OK;
+}
+
 static int decode_host(ldpc_decoder *d, const void *llr_v, int llr_bits, size_t frames, int32_t *iters, uint32_t *bits,
                        int32_t *post, int32_t *v2c)
 {
@@ -757,6 +883,20 @@ static int decode_host(ldpc_decoder *d, const void *llr_v, int llr_bits, size_t 
     CUDA_TRY(cudaSetDevice(d->device));
     const ldpc_code &c = d->code;
     const size_t nw32 = (c.n + 31) / 32, vsz = (size_t)c.dc_max * c.m;
+    {
+        // long batches without parity-mode outputs: the fed pipeline, 2^18 frames per launch
+        const ldpc::Plan &pl = d->cfg.precision == 32 ? d->plan32 : d->plan16;
+        const size_t per_grid = (size_t)d->sm_count * pl.kernel.ctas_per_sm * pl.W * (d->cfg.precision == 32 ? 1 : 2);
+        if (!post && !v2c && d->cfg.max_iter > 0 && frames >= 8 * per_grid && !getenv("LDPC_NO_FEED")) {
+            const size_t batch = (size_t)1 << 18;
+            for (size_t base = 0; base < frames; base += batch) {
+                const size_t cnt = std::min(batch, frames - base);
+                int rc = decode_host_fed(d, llr + base * c.n * esz, llr_bits, cnt, iters + base, bits ? bits + base * nw32 : nullptr);
+                if (rc != LDPC_OK) return rc;
+            }
+            return LDPC_OK;
+        }
+    }
     // Chunked pipeline: the H2D copy of chunk i+1, the decode of chunk i and the D2H copy of chunk i-1 overlap
     // (pinned host memory makes the copies asynchronous).  The first chunk is one frame per slot so that the
     // decode starts after a short copy; chunks then grow by half (the copy engine outruns the decoder by more than
@@ -884,6 +1024,8 @@ int ldpc_hard_decision_batch(ldpc_decoder *d, const int32_t *values, size_t fram
     d->cfg.max_iter = saved;
     return rc;
 }
+
+int ldpc_decoder_device(const ldpc_decoder *d) { return d ? d->device : LDPC_ERR_ARG; }
 
 int ldpc_decoder_sync(ldpc_decoder *d)
 {

@@ -55,6 +55,7 @@ struct KParams {
     int stage_rows;   // rows of shared memory that receive the channel values of the first claimed frames by
                       // cp.async.bulk (TMA 1-D) while the CTA decodes; 0: the refill reads global memory itself
     int stage_stride; // bytes per row buffer (16-byte multiple, >= one frame's values + 32)
+    int tables_bytes; // degree tables kept in shared memory between the control block and the stage rows
     // fed launches (host pipeline): frames [0, *avail) have arrived in `llr`; NULL: all of them
     const unsigned long long *avail;
     // fed launches: done_count[f / done_chunk] counts finished frames; the thread that completes a chunk sets the
@@ -187,8 +188,6 @@ struct Scalar32 {
         return (uint32_t)abs(val) | ((uint32_t)val & SIGN) | (val <= 0 ? HD : 0u);
     }
     __device__ static __forceinline__ void store_lane(uint32_t *word, int, uint32_t x) { *word = x; }
-    // all ones except in the lanes of word set w whose frame moved in this trip (`fresh`: one bit per slot)
-    __device__ static __forceinline__ uint32_t keep_mask(uint32_t fresh, int w) { return ((fresh >> w) & 1u) ? 0u : ALL; }
 };
 
 // Two frames per word (int16x2).  Exact as long as every |LLR|, |posterior| and |message| stays
@@ -292,11 +291,6 @@ struct Packed16 {
     __device__ static __forceinline__ void store_lane(uint32_t *word, int lane, uint32_t x)
     {
         reinterpret_cast<uint16_t *>(word)[lane] = (uint16_t)x;
-    }
-    __device__ static __forceinline__ uint32_t keep_mask(uint32_t fresh, int w)
-    {
-        const uint32_t b = fresh >> (2 * w);
-        return ~(((b & 1u) ? 0x0000ffffu : 0u) | ((b & 2u) ? 0xffff0000u : 0u));
     }
 };
 
@@ -411,13 +405,24 @@ struct Ctrl {
     unsigned int errs[MAX_SLOTS];  // info-bit errors of the frames being finished (MC mode)
     // Frames the CTA has claimed from the queue ahead of need: the entry with sequence number e lives in
     // q_fid[e % fifo_depth]; entries q_head .. q_head + fifo_depth - 1 exist, and those below q_staged have their
-    // channel values in stage row e % stage_rows (copy in flight or landed; mbarrier bar[row], phase (e / rows) & 1).
+    // channel values in stage row e % stage_rows (copy in flight or landed; mbarrier bar[row], phase parity q_par).
     // Written by thread 0 in the header update (between the two barriers of a trip), read by everybody after the
     // second one -- so all threads see the same queue when they plan a refill.
     int q_fid[MAX_FIFO];
+    unsigned char q_par[MAX_FIFO];      // staged entries: phase parity of their row's mbarrier for this use
+    unsigned char row_uses[MAX_STAGE];  // bulk copies issued into each row so far (mod 256)
     unsigned int q_head, q_staged;
     long long avail;                    // frames [0, avail) have arrived (fed launches; otherwise all)
     unsigned long long bar[MAX_STAGE];  // mbarriers of the stage rows
+    // State of the current trip (kept here rather than in registers: the two phases need every register they can get).
+    // Written before a barrier -- by thread 0, or by every thread with the same value -- and read behind it.
+    uint32_t active;    // slots that hold a frame
+    uint32_t served;    // slots the refill pass of this trip served (0: the trip had none)
+    uint32_t report;    // ... whose frame left in this trip
+    uint32_t taken;     // ... that received a frame
+    int ntake;          // entries taken from the queue of claimed frames
+    int drained;        // per-slot claims: the global queue is exhausted
+    unsigned long long claim;  // first of the `ntake` queue positions claimed to replace them
 };
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ------------------------------------------
@@ -442,6 +447,18 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// shared-memory layout: [W][E] message words | [W][n] channel words | control block (16-byte aligned) | degree tables of
+// irregular codes | stage rows (16-byte aligned; the host passes the tables' size)
+__device__ __forceinline__ Ctrl *ctrl_of(uint32_t *smem, int W, int E, int n)
+{
+    return reinterpret_cast<Ctrl *>((reinterpret_cast<uintptr_t>(smem + (size_t)W * (E + n)) + 15u) & ~(uintptr_t)15u);
+}
+__device__ __forceinline__ char *stage_of(uint32_t *smem, int W, int E, int n, const KParams &p)
+{
+    char *tables_end = reinterpret_cast<char *>(ctrl_of(smem, W, E, n) + 1) + p.tables_bytes;
+    return reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(tables_end) + 15u) & ~(uintptr_t)15u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -645,14 +662,10 @@ __device__ __forceinline__ void check_phase(const KParams &p, uint32_t *fail, ui
 // iteration's survive).
 // ------------------------------------------------------------------------------------------
 
-template <class T, int D, int NW, bool PARITY, bool ACC, bool MASK>
+template <class T, int D, int NW, bool PARITY, bool ACC>
 __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *gacc, char *base,
-                                               uint32_t stride, const uint32_t *off, uint32_t *llr, int v, int w, int n,
-                                               uint32_t fresh)
+                                               uint32_t stride, const uint32_t *off, uint32_t *llr, int v, int w, int n)
 {
-    // MASK: lanes whose frame moved in this trip (`fresh`) read their incoming messages as zero, which makes this
-    // phase the reference's initialisation for them (post = LLR, v2c = LLR, ArrayLDPC_Decoder.cpp:45-61) -- the words
-    // still hold the previous frame's messages, nothing clears them
     // ACC: gacc[] is the thread's running OR of the message words of word sets w, w+1, tested once per phase
     uint32_t x[NW][D > 0 ? D : 1], pw[NW], hd[NW], guard[NW], lx[NW];
 #pragma unroll
@@ -662,7 +675,6 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uin
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             x[i][j] = *reinterpret_cast<uint32_t *>(base + i * stride + off[j]);
-            if (MASK) x[i][j] &= T::keep_mask(fresh, w + i);
             T::acc_sub(acc, x[i][j]);
         }
         pw[i] = T::template post_word<D>(acc, hd[i]);
@@ -705,68 +717,67 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uin
     }
 }
 
-template <class T, int D, bool PARITY, bool MASK>
+template <class T, int D, bool PARITY>
 __device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
-                                              int v, int W, int n, int E, const uint32_t *off, uint32_t fresh)
+                                              int v, int W, int n, int E, const uint32_t *off)
 {
     char *base = reinterpret_cast<char *>(edge);
     const uint32_t stride = (uint32_t)E * 4u;
     int w = 0;
     if (D <= 12 && W == 3) {  // all three word sets of the CTA at once
-        variable_words<T, D, 3, PARITY, false, MASK>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, 0, n, fresh);
+        variable_words<T, D, 3, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, 0, n);
         return;
     }
     for (; w + 1 < W; w += 2, base += 2 * stride)
-        variable_words<T, D, 2, PARITY, false, MASK>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n, fresh);
-    if (w < W) variable_words<T, D, 1, PARITY, false, MASK>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n, fresh);
+        variable_words<T, D, 2, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
+    if (w < W) variable_words<T, D, 1, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
 }
 
 // the same with the guard bits of the first two word sets (all there are for the named codes) OR-ed into the
 // thread's accumulators instead of tested per variable; pays off for the short regular variable nodes
-template <class T, int D, bool PARITY, bool MASK>
+template <class T, int D, bool PARITY>
 __device__ __forceinline__ void variable_node_acc(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t (&gacc)[2], uint32_t *edge,
-                                                  uint32_t *llr, int v, int W, int n, int E, const uint32_t *off, uint32_t fresh)
+                                                  uint32_t *llr, int v, int W, int n, int E, const uint32_t *off)
 {
     char *base = reinterpret_cast<char *>(edge);
     const uint32_t stride = (uint32_t)E * 4u;
     if (W == 1) {
-        variable_words<T, D, 1, PARITY, true, MASK>(p, ctrl, gflag, gacc, base, stride, off, llr, v, 0, n, fresh);
+        variable_words<T, D, 1, PARITY, true>(p, ctrl, gflag, gacc, base, stride, off, llr, v, 0, n);
         return;
     }
-    variable_words<T, D, 2, PARITY, true, MASK>(p, ctrl, gflag, gacc, base, stride, off, llr, v, 0, n, fresh);
+    variable_words<T, D, 2, PARITY, true>(p, ctrl, gflag, gacc, base, stride, off, llr, v, 0, n);
     int w = 2;
     base += 2 * stride;
     for (; w + 1 < W; w += 2, base += 2 * stride)
-        variable_words<T, D, 2, PARITY, false, MASK>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n, fresh);
-    if (w < W) variable_words<T, D, 1, PARITY, false, MASK>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n, fresh);
+        variable_words<T, D, 2, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
+    if (w < W) variable_words<T, D, 1, PARITY, false>(p, ctrl, gflag, nullptr, base, stride, off, llr, v, w, n);
 }
 
-template <class T, int D, bool PARITY, bool MASK>
+template <class T, int D, bool PARITY>
 __device__ __forceinline__ void variable_node(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
-                                              int v, int W, int n, int E, uint32_t fresh)
+                                              int v, int W, int n, int E)
 {
     uint32_t off[D > 0 ? D : 1];  // byte offsets of the D edge words inside a word set
 #pragma unroll
     for (int j = 0; j < D; ++j) off[j] = (uint32_t)p.vedge[j * n + v] * 4u;
-    variable_node<T, D, PARITY, MASK>(p, ctrl, gflag, edge, llr, v, W, n, E, off, fresh);
+    variable_node<T, D, PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E, off);
 }
 
 // any degree (slow path for degrees without an exact instantiation): two passes over the words
 template <class T>
 __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
-                                                  int v, int W, int dv, int n, int E, uint32_t fresh)
+                                                  int v, int W, int dv, int n, int E)
 {
     for (int w = 0; w < W; ++w) {
         uint32_t *ew = edge + (size_t)w * E;
-        const uint32_t keep = T::keep_mask(fresh, w);
         const uint32_t lx = T::llr_restore(llr[(size_t)w * n + v]);
         typename T::Acc acc = T::acc_init(lx);
-        for (int j = 0; j < dv; ++j) T::acc_sub(acc, ew[p.vedge[(size_t)j * n + v]] & keep);
+        for (int j = 0; j < dv; ++j) T::acc_sub(acc, ew[p.vedge[(size_t)j * n + v]]);
         uint32_t hd, guard = 0;
         const uint32_t pw = T::template post_word<64>(acc, hd);
         for (int j = 0; j < dv; ++j) {
             uint32_t *q = &ew[p.vedge[(size_t)j * n + v]];
-            const uint32_t a = T::v2c_signmag(pw, *q & keep);
+            const uint32_t a = T::v2c_signmag(pw, *q);
             guard |= a;
             *q = a | hd;
         }
@@ -787,9 +798,9 @@ __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, 
 
 // REGV: every variable has degree DV -- the edge addresses of the thread's next variable are fetched while the
 // current one is processed (the table lives in global memory / L2)
-template <class T, int DV, bool PARITY, bool REGV, bool MASK>
+template <class T, int DV, bool PARITY, bool REGV>
 __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
-                                               int n, int E, const uint8_t *vdeg, uint32_t fresh)
+                                               int n, int E, const uint8_t *vdeg)
 {
     if (REGV) {
         uint32_t gacc[2] = {0u, 0u};  // guard bits of the thread's variables in word sets 0 and 1
@@ -804,7 +815,7 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
             const int vn = v + blockDim.x;
 #pragma unroll
             for (int j = 0; j < DV; ++j) next[j] = vn < n ? (uint32_t)p.vedge[j * n + vn] * 4u : 0u;
-            variable_node_acc<T, DV, PARITY, MASK>(p, ctrl, gflag, gacc, edge, llr, v, W, n, E, off, fresh);
+            variable_node_acc<T, DV, PARITY>(p, ctrl, gflag, gacc, edge, llr, v, W, n, E, off);
         }
         if (T::guard_hit(gacc[0])) atomicOr(&gflag[0], T::guard_lanes(gacc[0]));
         if (T::guard_hit(gacc[1])) atomicOr(&gflag[1], T::guard_lanes(gacc[1]));
@@ -819,17 +830,17 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
             if (DV <= 12) {
                 // exact-degree bodies: no per-edge predicates or branches inside
                 switch (dv) {
-#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), PARITY, MASK>(p, ctrl, gflag, edge, llr, v, W, n, E, fresh); done = true; } break;
+#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E); done = true; } break;
                     LDPC_VCASE(0) LDPC_VCASE(1) LDPC_VCASE(2) LDPC_VCASE(3) LDPC_VCASE(4) LDPC_VCASE(5) LDPC_VCASE(6)
                     LDPC_VCASE(7) LDPC_VCASE(8) LDPC_VCASE(9) LDPC_VCASE(10) LDPC_VCASE(11) LDPC_VCASE(12)
 #undef LDPC_VCASE
                 default: break;
                 }
             } else if (dv == DV) {
-                variable_node<T, DV, PARITY, MASK>(p, ctrl, gflag, edge, llr, v, W, n, E, fresh);
+                variable_node<T, DV, PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E);
                 done = true;
             }
-            if (!done) variable_node_any<T>(p, ctrl, gflag, edge, llr, v, W, dv, n, E, fresh);
+            if (!done) variable_node_any<T>(p, ctrl, gflag, edge, llr, v, W, dv, n, E);
         }
     }
 }
@@ -839,9 +850,9 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
 // check a*P + ((j - a*b) mod P), and sits in that check's slot b.  The word index b*m + a*P + t_a follows from
 // t_0 = j, t_(a+1) = t_a - b (mod P): two adds and an unsigned min per edge instead of a dependent table load from
 // L2 in a phase that is latency-bound (the host verifies the code against this formula before choosing the kernel).
-template <class T, int DV, int P, bool PARITY, bool MASK>
+template <class T, int DV, int P, bool PARITY>
 __device__ __forceinline__ void variable_phase_array(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
-                                                     int W, int n, int m, int E, uint32_t fresh)
+                                                     int W, int n, int m, int E)
 {
     uint32_t gacc[2] = {0u, 0u};
     constexpr uint32_t INV_P = (uint32_t)((1ull << 32) / P) + 1u;  // v / P == umulhi(v, INV_P) for v < 2^16
@@ -857,7 +868,7 @@ __device__ __forceinline__ void variable_phase_array(const KParams &p, Ctrl *ctr
             const uint32_t x = u - step;                // wraps to a huge value when t_a < b
             u = min(x, x + (uint32_t)(P * 4));
         }
-        variable_node_acc<T, DV, PARITY, MASK>(p, ctrl, gflag, gacc, edge, llr, v, W, n, E, off, fresh);
+        variable_node_acc<T, DV, PARITY>(p, ctrl, gflag, gacc, edge, llr, v, W, n, E, off);
     }
     if (T::guard_hit(gacc[0])) atomicOr(&gflag[0], T::guard_lanes(gacc[0]));
     if (W > 1 && T::guard_hit(gacc[1])) atomicOr(&gflag[1], T::guard_lanes(gacc[1]));
@@ -867,24 +878,10 @@ __device__ __forceinline__ void variable_phase_array(const KParams &p, Ctrl *ctr
 // register needs do not shape the allocation of the throughput path
 template <class T, int DV, bool REGV, int ARRP>
 __device__ __noinline__ void variable_phase_parity(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
-                                                   int n, int m, int E, const uint8_t *vdeg, uint32_t fresh)
+                                                   int n, int m, int E, const uint8_t *vdeg)
 {
-    if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), true, true>(p, ctrl, gflag, edge, llr, W, n, m, E, fresh);
-    else variable_phase<T, DV, true, REGV, true>(p, ctrl, gflag, edge, llr, W, n, E, vdeg, fresh);
-}
-
-// throughput path: the masked instantiation runs only in trips in which a frame moved in
-template <class T, int DV, bool REGV, int ARRP>
-__device__ __forceinline__ void variable_phase_fast(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
-                                                    int n, int m, int E, const uint8_t *vdeg, uint32_t fresh)
-{
-    if (fresh) {
-        if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), false, true>(p, ctrl, gflag, edge, llr, W, n, m, E, fresh);
-        else variable_phase<T, DV, false, REGV, true>(p, ctrl, gflag, edge, llr, W, n, E, vdeg, fresh);
-    } else {
-        if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), false, false>(p, ctrl, gflag, edge, llr, W, n, m, E, 0u);
-        else variable_phase<T, DV, false, REGV, false>(p, ctrl, gflag, edge, llr, W, n, E, vdeg, 0u);
-    }
+    if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), true>(p, ctrl, gflag, edge, llr, W, n, m, E);
+    else variable_phase<T, DV, true, REGV>(p, ctrl, gflag, edge, llr, W, n, E, vdeg);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -894,7 +891,8 @@ __device__ __forceinline__ void variable_phase_fast(const KParams &p, Ctrl *ctrl
 // while the queue still has frames) runs
 //     refill pass     every thread plans the refill from the control block (same answer in every thread, no barrier):
 //                     results of the frames that leave, channel values of the frames that move in; ONE barrier
-//     variable phase  lanes that just received a frame read their messages as zero (`fresh` mask): nothing is cleared
+//     variable phase  (the messages of a lane that received a frame were cleared by the refill pass, so this phase is
+//                     the reference's initialisation for it)
 //     [barrier]
 //     header update   slot owners / thread 0, while the other warps start the check phase: slot headers, Monte-Carlo
 //                     counters, the queue of claimed frames, bulk copies of the next frames into the stage rows
@@ -1007,31 +1005,30 @@ __device__ __forceinline__ Source planner_next(const KParams &p, const Ctrl *ctr
     if (f < 0) { pl.blocked = true; return Source{-1, -1, 0u}; }
     if (e < pl.staged) {
         ++pl.taken;
-        return Source{f, (int)(e % (unsigned int)p.stage_rows), (e / (unsigned int)p.stage_rows) & 1u};
+        return Source{f, (int)(e % (unsigned int)p.stage_rows), (uint32_t)ctrl->q_par[e % (unsigned int)p.fifo_depth]};
     }
     if (p.mc_mode == 0 && (long long)f >= pl.avail) { pl.blocked = true; return Source{-1, -1, 0u}; }
     ++pl.taken;
     return Source{f, -1, 0u};
 }
 
-// What a refill pass did, for the header update that follows it.
-struct Refill {
-    uint32_t taken;             // slots that received a frame
-    int ntake;                  // entries taken from the CTA's queue
-    unsigned long long claim;   // thread 0: first of the `ntake` queue positions claimed to replace them
-    bool drained;               // sync claims only: the queue is exhausted
-};
-
+// The refill pass of a trip.  `want`: slots to serve (frames that stopped at the last decision, idle slots asking for a
+// frame); `sync`: per-slot claims (first fill, short queues) instead of the CTA's queue of claimed frames.  Leaves
+// what it did in ctrl->served / report / taken / ntake / claim / active / drained for the header update and the stop
+// decision (ctrl->active itself is rewritten by the header update: every thread reads it here), and ends with the
+// barrier behind which the variable phase may run.  Returns the slots that hold a frame after the pass.
 template <class T>
-__device__ __noinline__ Refill refill_pass(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr, char *stage,
-                                              uint32_t want, uint32_t active, bool sync, int n, int E, int W,
-                                              long long frames, unsigned int trip, int buf)
+__device__ __noinline__ uint32_t refill_pass(const KParams &p, uint32_t *smem, uint32_t want, bool sync, int n, int E, int W,
+                                             unsigned int trip, int buf)
 {
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int nslots = W * T::LANES;
-    const uint32_t report = want & active;  // slots whose frame leaves
+    uint32_t *edge = smem, *llr = smem + (size_t)W * E;
+    Ctrl *ctrl = ctrl_of(smem, W, E, n);
+    const long long frames = p.count ? (long long)*p.count : p.frames;
+    const uint32_t before = ctrl->active;
+    const uint32_t report = want & before;  // slots whose frame leaves
     const bool mine = tid < nslots && ((want >> tid) & 1u);  // one thread per slot (all in warp 0)
-    Refill out{0u, 0, 0ull, false};
     if (mine && ((report >> tid) & 1u)) {
         const int s = tid, w = s / T::LANES, lane = s % T::LANES;
         const bool was_over = (ctrl->gflag[buf][w] >> lane) & 1u;
@@ -1050,23 +1047,31 @@ __device__ __noinline__ Refill refill_pass(const KParams &p, Ctrl *ctrl, uint32_
         __syncthreads();
     }
     // ---- plan (identical in every thread)
+    uint32_t taken = 0;
+    int ntake = 0;
+    bool drained = false;
     {
         Planner pl = planner_init(ctrl);
         for (uint32_t left = want; left; left &= left - 1u) {
             const int s = __ffs(left) - 1;
             const Source src = planner_next(p, ctrl, pl, s, sync);
-            if (src.fn >= 0) out.taken |= 1u << s;
-            else if (sync) out.drained = true;
+            if (src.fn >= 0) taken |= 1u << s;
+            else if (sync) drained = true;
             if (mine && s == tid) {
                 if (!sync) ctrl->newfid[s] = src.fn;
                 if (p.mc_mode == 2 && src.fn >= 0)
                     ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed, lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)src.fn));
             }
         }
-        out.ntake = pl.taken;
+        ntake = pl.taken;
     }
-    // the positions that replace the entries taken: the atomic's round trip overlaps this pass and the variable phase
-    if (!sync && tid == 0 && out.ntake > 0) out.claim = atomicAdd(p.queue, (unsigned long long)out.ntake);
+    if (tid == 0) {
+        // the positions that replace the entries taken: the atomic's round trip overlaps this pass and the variable phase
+        unsigned long long claim = 0;
+        if (!sync && ntake > 0) claim = atomicAdd(p.queue, (unsigned long long)ntake);
+        ctrl->served = want; ctrl->report = report; ctrl->taken = taken; ctrl->ntake = ntake; ctrl->claim = claim;
+        ctrl->drained |= drained ? 1 : 0;
+    }
 
     const bool emit = p.bits || p.mc_mode != 0;
     if (p.mc_mode != 0) {
@@ -1092,7 +1097,7 @@ __device__ __noinline__ Refill refill_pass(const KParams &p, Ctrl *ctrl, uint32_
         const int w = s / T::LANES, lane = s % T::LANES;
         const Source src = planner_next(p, ctrl, pl, s, sync);
         const int fn = src.fn;
-        uint32_t *lw = llr + (size_t)w * n;
+        uint32_t *ew = edge + (size_t)w * E, *lw = llr + (size_t)w * n;
         if (p.mc_mode == 0) {
             const int fo = (emit && ((report >> s) & 1u)) ? ctrl->fid[s] : -1;
             uint32_t *bits_out = fo >= 0 ? p.bits + (size_t)fo * p.nw32 : nullptr;
@@ -1103,7 +1108,7 @@ __device__ __noinline__ Refill refill_pass(const KParams &p, Ctrl *ctrl, uint32_
                 // below the frame's first byte
                 mbar_wait(&ctrl->bar[src.row], src.parity);
                 const uintptr_t first = reinterpret_cast<uintptr_t>(p.llr) + (size_t)fn * n * 2u;
-                const int16_t *row = reinterpret_cast<const int16_t *>(stage + (size_t)src.row * p.stage_stride + (first & 15u));
+                const int16_t *row = reinterpret_cast<const int16_t *>(stage_of(smem, W, E, n, p) + (size_t)src.row * p.stage_stride + (first & 15u));
                 bad = swap_frame<T>(lw, lane, bits_out, row, n);
             } else if (p.llr_bits == 16) {
                 bad = swap_frame<T>(lw, lane, bits_out, fn >= 0 ? reinterpret_cast<const int16_t *>(p.llr) + (size_t)fn * n : nullptr, n);
@@ -1135,12 +1140,16 @@ __device__ __noinline__ Refill refill_pass(const KParams &p, Ctrl *ctrl, uint32_
                 if (bad) bad_slots |= 1u << s;
             }
         }
+        // the messages of a lane that received a frame start from zero: the coming variable phase then computes
+        // post = LLR, v2c = LLR for it -- the reference's initialisation (ArrayLDPC_Decoder.cpp:45-61)
+        if (fn >= 0 && trip != 0u)
+            for (int i = tid; i < E; i += nthreads) T::store_lane(&ew[i], lane, 0u);
     }
-    if (p.mc_mode != 0 && p.mc_pin_count > 0 && out.taken) {  // shortening: known positions pinned (PerfTest.cpp:410-414)
+    if (p.mc_mode != 0 && p.mc_pin_count > 0 && taken) {  // shortening: known positions pinned (PerfTest.cpp:410-414)
         __syncthreads();
         for (int i = tid; i < p.mc_pin_count; i += nthreads) {
             const int v = p.mc_pin[i];
-            for (uint32_t left = out.taken; left; left &= left - 1u) {
+            for (uint32_t left = taken; left; left &= left - 1u) {
                 const int s = __ffs(left) - 1;
                 bool bad;
                 T::store_lane(&llr[(size_t)(s / T::LANES) * n + v], s % T::LANES, T::llr_lane(p.mc_pin_value, bad));
@@ -1150,9 +1159,8 @@ __device__ __noinline__ Refill refill_pass(const KParams &p, Ctrl *ctrl, uint32_
     }
     for (int s = 0; bad_slots; ++s, bad_slots >>= 1)  // judged by the coming trip's stop decision
         if (bad_slots & 1u) atomicOr(&ctrl->gflag[buf == 2 ? 0 : buf + 1][s / T::LANES], 1u << (s % T::LANES));
-    (void)edge; (void)E;
     __syncthreads();
-    return out;
+    return (before & ~want) | taken;
 }
 
 // After a refill pass, between the barrier that ends the variable phase and the check phase (parity-mode launches:
@@ -1163,12 +1171,15 @@ __device__ __noinline__ Refill refill_pass(const KParams &p, Ctrl *ctrl, uint32_
 //                values of the first `stage_rows` entries into their stage rows, the fed launch's arrival mark
 //   warp 0       L2 prefetch of the channel values the refill will read from global memory
 template <class T>
-__device__ __noinline__ void header_update(const KParams &p, Ctrl *ctrl, char *stage, uint32_t want, uint32_t active_before,
-                                              const Refill &rf, bool sync, int n, int W, long long frames, unsigned int trip, int rbuf)
+__device__ __noinline__ void header_update(const KParams &p, uint32_t *smem, bool sync, int n, int E, int W, unsigned int trip, int rbuf)
 {
     const int tid = threadIdx.x, lane_id = tid & 31;
     const int nslots = W * T::LANES;
-    const uint32_t report = want & active_before;
+    Ctrl *ctrl = ctrl_of(smem, W, E, n);
+    const long long frames = p.count ? (long long)*p.count : p.frames;
+    const uint32_t want = ctrl->served, report = ctrl->report, taken = ctrl->taken;
+    const int ntake = ctrl->ntake;
+    if (tid == 0) ctrl->active = (ctrl->active & ~want) | taken;  // (the refill pass read the old value before its barrier)
     if (tid < nslots && ((want >> tid) & 1u)) {
         const int s = tid;
         if ((report >> s) & 1u) {
@@ -1197,7 +1208,7 @@ __device__ __noinline__ void header_update(const KParams &p, Ctrl *ctrl, char *s
             }
         }
         ctrl->errs[s] = 0u;
-        ctrl->fid[s] = ((rf.taken >> s) & 1u) ? ctrl->newfid[s] : -1;
+        ctrl->fid[s] = ((taken >> s) & 1u) ? ctrl->newfid[s] : -1;
         ctrl->start[s] = trip;  // its first (initialising) variable phase runs in this trip
     }
     if (sync && !p.claim_ahead) return;
@@ -1209,9 +1220,10 @@ __device__ __noinline__ void header_update(const KParams &p, Ctrl *ctrl, char *s
             const unsigned long long base = atomicAdd(p.queue, (unsigned long long)L);
             for (unsigned int k = 0; k < L; ++k) ctrl->q_fid[k] = queue_frame(p, base + k, frames);
         } else {
-            for (int k = 0; k < rf.ntake; ++k)
-                ctrl->q_fid[(head + L + (unsigned int)k) % L] = queue_frame(p, rf.claim + (unsigned long long)k, frames);
-            head += (unsigned int)rf.ntake;
+            const unsigned long long claim = ctrl->claim;
+            for (int k = 0; k < ntake; ++k)
+                ctrl->q_fid[(head + L + (unsigned int)k) % L] = queue_frame(p, claim + (unsigned long long)k, frames);
+            head += (unsigned int)ntake;
             ctrl->q_head = head;
         }
         const long long avail = frames_arrived(p, frames);
@@ -1219,6 +1231,7 @@ __device__ __noinline__ void header_update(const KParams &p, Ctrl *ctrl, char *s
         unsigned int staged = max(ctrl->q_staged, head);
         if (S > 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the rows were read through the generic proxy
+            char *stage = stage_of(smem, W, E, n, p);
             const size_t bytes = (size_t)n * 2u;
             for (; staged < head + S; ++staged) {
                 const int f = ctrl->q_fid[staged % L];
@@ -1227,19 +1240,21 @@ __device__ __noinline__ void header_update(const KParams &p, Ctrl *ctrl, char *s
                 const uintptr_t lo = first & ~(uintptr_t)15u;
                 const uint32_t len = (uint32_t)(((first + bytes + 15u) & ~(uintptr_t)15u) - lo);
                 unsigned long long *bar = &ctrl->bar[staged % S];
+                ctrl->q_par[staged % L] = ctrl->row_uses[staged % S] & 1u;  // a row is skipped when its entry is read directly
+                ctrl->row_uses[staged % S]++;
                 mbar_expect_tx(bar, len);
                 bulk_copy_g2s(stage + (size_t)(staged % S) * p.stage_stride, reinterpret_cast<const void *>(lo), len, bar);
             }
         }
         ctrl->q_staged = staged;
     }
-    if (!sync && p.mc_mode == 0 && tid < 32 && rf.ntake > 0 && p.stage_rows < p.fifo_depth) {
+    if (!sync && p.mc_mode == 0 && tid < 32 && ntake > 0 && p.stage_rows < p.fifo_depth && !p.avail) {
         // entries that will not be staged: pull their channel values into L2, they are read a frame time from now
-        const unsigned long long claim = __shfl_sync(0xffffffffu, rf.claim, 0);
+        const unsigned long long claim = ctrl->claim;
         const size_t bytes = (size_t)n * (p.llr_bits >> 3);
-        for (int k = 0; k < rf.ntake; ++k) {
+        for (int k = 0; k < ntake; ++k) {
             const int f = queue_frame(p, claim + (unsigned long long)k, frames);
-            if (f >= 0 && !p.avail) {
+            if (f >= 0) {
                 const char *first_byte = reinterpret_cast<const char *>(p.llr) + (size_t)f * bytes;
                 const char *line = first_byte - (reinterpret_cast<uintptr_t>(first_byte) & 127u) + (size_t)lane_id * 128u;
                 for (; line < first_byte + bytes; line += 32 * 128) prefetch_l2(line);
@@ -1256,10 +1271,10 @@ __device__ __noinline__ void header_update(const KParams &p, Ctrl *ctrl, char *s
 // every thread and no barrier is needed to agree on it.  Idle slots ask for a frame while the CTA's queue of
 // claimed frames has one.
 template <class T>
-__device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, int W, uint32_t active, bool fifo,
-                                                  unsigned int trip, int buf)
+__device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, int W, bool fifo, unsigned int trip, int buf)
 {
     const int s = threadIdx.x & 31;
+    const uint32_t active = ctrl->active;
     bool stop = false;
     if (s < W * T::LANES) {
         if ((active >> s) & 1u) {
@@ -1270,6 +1285,8 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
             stop = it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over;
         } else if (fifo) {
             stop = ctrl->q_fid[ctrl->q_head % (unsigned int)p.fifo_depth] >= 0;
+        } else {
+            stop = !ctrl->drained;  // short queue: idle slots claim for themselves while frames are left
         }
     }
     const uint32_t fin = __ballot_sync(0xffffffffu, stop);
@@ -1279,6 +1296,7 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
         ctrl->fail[clr][threadIdx.x] = 0u;
         ctrl->gflag[clr][threadIdx.x] = 0u;
     }
+    if (threadIdx.x == 0 && fin == 0u) ctrl->served = 0u;  // no refill pass in the coming trip
     return fin;
 }
 
@@ -1313,19 +1331,15 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
     const int n = N ? N : p.n, m = M ? M : p.m, E = EA ? EA : (M ? DC * M : p.E), W = p.W;
     uint32_t *edge = smem;                 // [W][E]
     uint32_t *llr = edge + (size_t)W * E;  // [W][n] channel values (+ the hard decision of the last posterior)
-    Ctrl *ctrl = reinterpret_cast<Ctrl *>((reinterpret_cast<uintptr_t>(llr + (size_t)W * n) + 15u) & ~(uintptr_t)15u);
-    // degree tables next to the control block (irregular codes dispatch on them once per node and phase)
+    Ctrl *ctrl = ctrl_of(smem, W, E, n);
+    // degree tables next to the control block (irregular codes dispatch on them once per node and phase); the stage
+    // rows follow them (stage_of)
     constexpr bool REGV = PREFETCH_VEDGE && M != 0 && REG && DV <= 8 && ARRP == 0;
     uint8_t *cdeg_s = reinterpret_cast<uint8_t *>(ctrl + 1);
     uint8_t *vdeg_s = cdeg_s + (REG ? 0 : ((m + 15) & ~15));
-    uint8_t *tables_end = vdeg_s + ((REGV || ARRP) ? 0 : ((n + 15) & ~15));
-    // stage rows: 16-byte aligned, after the tables
-    char *stage = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(tables_end) + 15u) & ~(uintptr_t)15u);
     if (!REG) for (int i = tid; i < m; i += nthreads) cdeg_s[i] = p.cdeg[i];
     if (!REGV && !ARRP) for (int i = tid; i < n; i += nthreads) vdeg_s[i] = p.vdeg[i];
     const int nslots = W * T::LANES;
-    const long long frames = p.count ? (long long)*p.count : p.frames;
-    const bool parity_out = p.post || p.v2c;
 
     for (int i = tid; i < W * (E + n); i += nthreads) smem[i] = 0u;
     if (tid < MAX_W)
@@ -1333,10 +1347,11 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
     if (tid < MAX_SLOTS) {
         ctrl->fid[tid] = -1; ctrl->start[tid] = 0u; ctrl->newfid[tid] = -1; ctrl->errs[tid] = 0u; ctrl->lehmer[tid] = 0u;
     }
-    if (tid < MAX_FIFO) ctrl->q_fid[tid] = -1;
+    if (tid < MAX_FIFO) { ctrl->q_fid[tid] = -1; ctrl->q_par[tid] = 0; }
     if (tid == 0) {
         ctrl->q_head = 0u; ctrl->q_staged = 0u; ctrl->avail = 0;
-        for (int r = 0; r < MAX_STAGE; ++r) mbar_init(&ctrl->bar[r], 1u);
+        ctrl->active = 0u; ctrl->served = 0u; ctrl->report = 0u; ctrl->taken = 0u; ctrl->ntake = 0; ctrl->drained = 0; ctrl->claim = 0ull;
+        for (int r = 0; r < MAX_STAGE; ++r) { mbar_init(&ctrl->bar[r], 1u); ctrl->row_uses[r] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1349,58 +1364,50 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
 #define LDPC_MARK(k) do { } while (0)
 #endif
 
-    const uint32_t all_slots = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);
-    uint32_t want = all_slots;  // slots to serve at the top of the trip: stopped frames, idle slots
-    uint32_t active = 0u;       // slots that hold a frame
-    bool sync = true;           // the first fill claims per slot; later refills take the frames claimed ahead
-    bool drained = false;       // sync claims: the queue is exhausted
-    // trip t votes into buffer t % 3; `buf` is the buffer of the trip that ended last (what a refill reports from)
+    // slots to serve at the top of the trip: stopped frames, idle slots asking for a frame
+    uint32_t want = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);
+    // trip t votes into buffer t % 3; `buf` is the buffer of the trip that ended last (what a refill reports from).
+    // The first fill (trip 0) claims per slot; later refills take the frames the CTA claimed ahead.
     unsigned int trip = 0;
     int buf = 2;
     for (;;) {
-        Refill rf{0u, 0, 0ull, false};
-        const uint32_t before = active;
-        const uint32_t served = want;
-        const bool served_sync = sync;
-        if (served) {
-            rf = refill_pass<T>(p, ctrl, edge, llr, stage, served, before, sync, n, E, W, frames, trip, buf);
-            active = (active & ~served) | rf.taken;
-            drained |= rf.drained;
-        }
-        const int rbuf = buf;
-        if (!active) {
+        const bool sync = trip == 0u || !p.claim_ahead;
+        uint32_t holding = 1u;
+        if (want) holding = refill_pass<T>(p, smem, want, sync, n, E, W, trip, buf);
+        if (!holding) {
             // nothing to decode right now: finish the bookkeeping, then either leave or (fed launch whose next
             // frames have not arrived yet) look again
-            if (served || p.claim_ahead) header_update<T>(p, ctrl, stage, served, before, rf, served_sync, n, W, frames, trip, rbuf);
+            if (want || p.claim_ahead) header_update<T>(p, smem, sync, n, E, W, trip, buf);
             __syncthreads();
-            const bool more = p.claim_ahead ? ctrl->q_fid[ctrl->q_head % (unsigned int)p.fifo_depth] >= 0 : !drained;
+            const bool more = p.claim_ahead ? ctrl->q_fid[ctrl->q_head % (unsigned int)p.fifo_depth] >= 0 : !ctrl->drained;
             if (!more) break;
             __syncthreads();  // q_* were read above; thread 0 rewrites them in the next header update
             __nanosleep(500);
-            want = all_slots;
-            sync = !p.claim_ahead;
+            want = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);
+            ++trip;
             continue;
         }
+        const int rbuf = buf;
         buf = buf == 2 ? 0 : buf + 1;
         LDPC_MARK(0);
-        if (parity_out) {
-            if (served) {
-                header_update<T>(p, ctrl, stage, served, before, rf, served_sync, n, W, frames, trip, rbuf);
+        if (p.post || p.v2c) {
+            if (ctrl->served) {  // the parity-mode variable phase looks up the frame of every lane
+                header_update<T>(p, smem, sync, n, E, W, trip, rbuf);
                 __syncthreads();
             }
-            variable_phase_parity<T, DV, REGV, ARRP>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s, rf.taken);
+            variable_phase_parity<T, DV, REGV, ARRP>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s);
+        } else if (ARRP) {
+            variable_phase_array<T, DV, (ARRP ? ARRP : 1), false>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E);
         } else {
-            variable_phase_fast<T, DV, REGV, ARRP>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s, rf.taken);
+            variable_phase<T, DV, false, REGV>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s);
         }
         __syncthreads();
         LDPC_MARK(1);
-        if (served && !parity_out) header_update<T>(p, ctrl, stage, served, before, rf, served_sync, n, W, frames, trip, rbuf);
+        if (ctrl->served && !(p.post || p.v2c)) header_update<T>(p, smem, sync, n, E, W, trip, rbuf);
         check_phase<T, DC, REG, NI>(p, ctrl->fail[buf], edge, cdeg_s, items, m, E, W);
         __syncthreads();
         LDPC_MARK(2);
-        sync = !p.claim_ahead;
-        want = stop_decision<T>(p, ctrl, W, active, !sync, trip, buf);
-        if (sync && !drained) want |= all_slots & ~active;  // short queue: idle slots claim for themselves
+        want = stop_decision<T>(p, ctrl, W, p.claim_ahead != 0, trip, buf);
         ++trip;
         LDPC_MARK(3);
     }

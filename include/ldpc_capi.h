@@ -130,6 +130,9 @@ int ldpc_decode_batch_device(ldpc_decoder *dec, const void *d_llr, int llr_bits,
  * `values` are channel LLRs (hardDecision) or posteriors (checkPost*). */
 int ldpc_hard_decision_batch(ldpc_decoder *dec, const int32_t *values, size_t frames, int32_t *fail, uint32_t *bits);
 
+/* CUDA device ordinal the decoder is bound to. */
+int ldpc_decoder_device(const ldpc_decoder *dec);
+
 /* Blocks until everything queued on the decoder's streams has finished. */
 int ldpc_decoder_sync(ldpc_decoder *dec);
 
@@ -229,6 +232,49 @@ int ldpc_mc_run(ldpc_decoder *dec, const ldpc_mc_cfg *cfg, size_t frames, uint16
  * accumulated into (the caller zeroes it). */
 int ldpc_mc_run_device(ldpc_decoder *dec, const ldpc_mc_cfg *cfg, size_t frames, uint16_t *d_frame_err,
                        int32_t *d_iters, uint64_t *d_counters, void *stream);
+
+/* ------------------------------------------------------------------ Monte-Carlo point on all GPUs of the box */
+
+/* Stopping rule of the reference's frame loops, applied to the frames in global index order, so that the counters are
+ * the ones the sequential loop produces whatever the number of GPUs and the batch size:
+ *   target_block_errors  `while(pckerror < 100)`   (PerfTest.cpp:97, 276, 385, 491); 0 = none
+ *   max_frames           `while(Counter < MaxPckNum)` (PerfTest.cpp:580); 0 = none
+ * count_iterations: ArrayLDPC_PerfTest / ArrayLDPC_TimeTrial take the decoder's return value as the block's error
+ * count (quirk Q9, PerfTest.cpp:507-511, 596-600) instead of calculateBER's. */
+typedef struct {
+    uint64_t target_block_errors;
+    uint64_t max_frames;
+    size_t frames_per_round;   /* frames per GPU and round (0 = 131072)                                            */
+    int count_iterations;
+    int32_t *iters_out;        /* optional host buffer [iters_cap]: the decoder's return value of every counted    */
+    size_t iters_cap;          /*   frame, in frame order (ArrayLDPC_Debug_Shorten prints them, PerfTest.cpp:419)   */
+} ldpc_mc_stop;
+
+typedef struct {
+    uint64_t frames;           /* Counter                                                                           */
+    uint64_t block_errors;     /* pckerror                                                                          */
+    uint64_t errors;           /* biterror (or the iteration sum under count_iterations)                            */
+    uint64_t iter_sum;         /* sum of the decoder's return values over the counted frames                        */
+    uint64_t iter_hist[32];    /* frames per return value 0..31                                                     */
+    uint64_t rounds;           /* rounds (= counter all-reduces) executed                                           */
+    int reached;               /* 1: stopped on target_block_errors                                                 */
+    int devices;
+    double seconds;            /* wall time of the run                                                              */
+} ldpc_mc_result;
+
+typedef struct ldpc_mc_group ldpc_mc_group;
+
+/* One decoder handle per GPU (all for the same code and configuration, each on its own device).  Creates the NCCL
+ * communicator over those devices (none for a single one) and one host thread per device per run.  Device r of R
+ * simulates the frames [(round*R + r)*B, +B) of every round; per round the counters travel through ONE ncclAllReduce
+ * (320 bytes over NVLink), per-frame results only in the final round. */
+ldpc_mc_group *ldpc_mc_group_create(ldpc_decoder *const *decoders, int ndev, int *err);
+int ldpc_mc_group_size(const ldpc_mc_group *group);
+int ldpc_mc_group_run(ldpc_mc_group *group, const ldpc_mc_cfg *cfg, const ldpc_mc_stop *stop, ldpc_mc_result *result);
+void ldpc_mc_group_destroy(ldpc_mc_group *group);
+/* create + run + destroy */
+int ldpc_mc_run_multi(ldpc_decoder *const *decoders, int ndev, const ldpc_mc_cfg *cfg, const ldpc_mc_stop *stop,
+                      ldpc_mc_result *result);
 
 /* Channel only: the quantised LLRs [frames][n] the simulation above would decode (host buffer). */
 int ldpc_mc_channel(ldpc_decoder *dec, const ldpc_mc_cfg *cfg, size_t frames, int32_t *llr);

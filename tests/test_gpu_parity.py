@@ -316,3 +316,34 @@ def test_int16_host_entry_equals_int32_host_entry(fp, po, name):
             assert (post == b["post"][f]).all()
     assert dec.stats()["fallback_frames"] >= 1
     dec.close()
+
+
+@pytest.mark.parametrize("name,bits16", [("wifi", False), ("wifi", True), ("a5", True)])
+def test_fed_host_pipeline_equals_chunked_pipeline(fp, po, name, bits16):
+    """Long host batches run as ONE persistent launch fed by chunked copies (arrival mark polled by the kernel, results
+    copied out per finished chunk); short ones as chunked launches.  Same results, including frames that leave the packed
+    guard range (re-decoded by the int32 kernel after the fed launch, results copied again) and the oracle's."""
+    import os
+    code = fp.codes.NAMED[name]()
+    t = tables_of(code)
+    rate = fp.codes.INFO_BITS[name] / code.n
+    frames = 40000
+    llr = channel_frames(code.n, rate, 2.0 if name == "wifi" else 4.0, frames, seed=4242)
+    for f in (5, 20000, frames - 1):
+        llr[f] = np.clip(llr[f] * 40, -32768, 32767)
+    dec = fp.Decoder(code, precheck=(name == "a5"))
+    run = (lambda: dec.decode_i16(llr.astype(np.int16))) if bits16 else (lambda: dec.decode(llr))
+    os.environ.pop("LDPC_NO_FEED", None)
+    a = run()
+    os.environ["LDPC_NO_FEED"] = "1"
+    try:
+        b = run()
+    finally:
+        os.environ.pop("LDPC_NO_FEED", None)
+    assert (a["iters"] == b["iters"]).all() and (a["bits"] == b["bits"]).all()
+    assert dec.stats()["fallback_frames"] >= 3
+    orc = po.Oracle(t)
+    for f in (0, 5, 1234, 20000, frames - 1):
+        it, bits, _, _ = orc.decode(llr[f], precheck=(name == "a5"))
+        assert it == a["iters"][f] and (fp.unpack_bits(a["bits"][f:f + 1], code.n)[0] == bits).all()
+    dec.close()
