@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libldpc_b200.so")
-SOURCES = ["ldpc_decoder.cu", "ldpc_encode.cu", "ldpc_multi.cu", "ldpc_code.cpp"]
+SOURCES = ["ldpc_decoder.cu", "ldpc_encode.cu", "ldpc_multi.cu", "ldpc_decode_f64.cu", "ldpc_code.cpp"]
 HEADERS = ["ldpc_kernels.cuh", "ldpc_code.hpp", os.path.join("..", "..", "include", "ldpc_capi.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

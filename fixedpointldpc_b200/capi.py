@@ -23,7 +23,7 @@ EXPORTS = (
     "ldpc_decoder_cfg_default", "ldpc_decoder_create", "ldpc_decoder_destroy", "ldpc_decode_batch", "ldpc_decode_batch_i16",
     "ldpc_decode_batch_device", "ldpc_decoder_sync", "ldpc_decoder_get_stats", "ldpc_device_count",
     "ldpc_mc_run", "ldpc_mc_run_device", "ldpc_mc_channel", "ldpc_hard_decision_batch",
-    "ldpc_decoder_device", "ldpc_mc_group_create", "ldpc_mc_group_size", "ldpc_mc_group_run", "ldpc_mc_group_destroy",
+    "ldpc_decoder_device", "ldpc_decoder_code", "ldpc_decoder_max_iter", "ldpc_decode_batch_f64", "ldpc_mc_group_create", "ldpc_mc_group_size", "ldpc_mc_group_run", "ldpc_mc_group_destroy",
     "ldpc_mc_run_multi",
     "ldpc_encode_batch", "ldpc_encode_batch_device", "ldpc_gen_load", "ldpc_gen_from_code", "ldpc_gen_save", "ldpc_gen_free", "ldpc_gen_dims", "ldpc_gen_indices", "ldpc_gen_encode",
 )
@@ -113,6 +113,10 @@ def load_library():
     L.ldpc_mc_run_device.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp, vp, vp, vp]
     L.ldpc_mc_channel.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp]
     L.ldpc_decoder_device.argtypes = [vp]
+    L.ldpc_decoder_code.restype = vp
+    L.ldpc_decoder_code.argtypes = [vp]
+    L.ldpc_decoder_max_iter.argtypes = [vp]
+    L.ldpc_decode_batch_f64.argtypes = [vp, vp, C.c_size_t, vp, vp, vp, vp]
     L.ldpc_mc_group_create.restype = vp
     L.ldpc_mc_group_create.argtypes = [C.POINTER(vp), C.c_int, ip]
     L.ldpc_mc_group_size.argtypes = [vp]
@@ -294,6 +298,18 @@ class Decoder:
                                                 _ptr(out["post"]), _ptr(out["v2c"])))
         return out
 
+    def decode_f64(self, llr, want_post=True, want_v2c=False):
+        """FP_Decoder::decode_general(const double *): llr float64 [frames][n]; returns dict(iters, bits, post, v2c)."""
+        c = self.code
+        llr = np.ascontiguousarray(llr, np.float64).reshape(-1, c.n)
+        f = len(llr)
+        out = {"iters": np.zeros(f, np.int32), "bits": np.zeros((f, c.nw32), np.uint32),
+               "post": np.zeros((f, c.n), np.float64) if want_post else None,
+               "v2c": np.zeros((f, c.dc_max, c.m), np.float64) if want_v2c else None}
+        _check(load_library().ldpc_decode_batch_f64(self._h, _ptr(llr), f, _ptr(out["iters"]), _ptr(out["bits"]),
+                                                    _ptr(out["post"]), _ptr(out["v2c"])))
+        return out
+
     def decode_raw(self, llr_ptr, frames, iters_ptr, bits_ptr=None, post_ptr=None, v2c_ptr=None, llr_bits=32):
         """Host-pointer call (pinned buffers for the end-to-end timing); llr_bits = 32 (`const int *LLR`) or 16."""
         fn = load_library().ldpc_decode_batch if llr_bits == 32 else load_library().ldpc_decode_batch_i16
@@ -400,6 +416,19 @@ class McGroup:
     def __init__(self, decoders):
         L = load_library()
         self.decoders = list(decoders)
+        if len(self.decoders) > 1 and "LDPC_NCCL_LIB" not in os.environ:
+            # one NCCL per process: prefer the one PyTorch ships (same soname as the system's), located without
+            # importing torch
+            import importlib.util
+            try:
+                spec = importlib.util.find_spec("nvidia.nccl")
+                for root in (spec.submodule_search_locations if spec else []):
+                    cand = os.path.join(root, "lib", "libnccl.so.2")
+                    if os.path.exists(cand):
+                        os.environ["LDPC_NCCL_LIB"] = cand
+                        break
+            except Exception:
+                pass
         arr = (C.c_void_p * len(self.decoders))(*[d._h for d in self.decoders])
         err = C.c_int()
         self._h = L.ldpc_mc_group_create(arr, len(self.decoders), C.byref(err))

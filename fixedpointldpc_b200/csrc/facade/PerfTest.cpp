@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <fstream>
 #include <iostream>
@@ -54,17 +55,34 @@ struct Point {
     double biterror, pckerror;
     long Counter;
     unsigned long long iter_sum;
+    unsigned long long iter_hist[32];  // frames per decoder return value
+    int devices;
+    double seconds;
 };
 
 enum Rule { COUNT_INFO_BIT_ERRORS, COUNT_ITERATIONS };
 
-// The frame loop shared by all drivers.  stop_errors: `while(pckerror < stop_errors)`; max_frames:
-// `while(Counter < MaxPckNum)`.  Returns the reference's three counters.
+// GPUs the frame loops run on: all visible ones, or the first LDPC_GPUS of them
+int gpu_count()
+{
+    int n = ldpc_device_count();
+    if (n < 1) ldpc_facade::fail("no CUDA device", n < 0 ? n : LDPC_ERR_NO_DEVICE);
+    const char *env = getenv("LDPC_GPUS");
+    if (env && atoi(env) > 0 && atoi(env) < n) n = atoi(env);
+    return n;
+}
+
+// The frame loop shared by all drivers, on all GPUs of the box (ldpc_mc_group_run: device r of R simulates the frames
+// [(round*R + r)*B, +B) of every round, the counters are all-reduced over NCCL once per round, and the run is cut on
+// exactly the frame on which the reference's sequential loop stops).  stop_errors: `while(pckerror < stop_errors)`;
+// max_frames: `while(Counter < MaxPckNum)`.  Returns the reference's three counters.
 Point simulate(FP_Decoder &Decoder, bool fixpoint, double snr, double sigma, const std::vector<uint8_t> *codeword,
                const std::vector<int32_t> *info_index, const std::vector<int32_t> *pins, int pin_value, Rule rule,
                long stop_errors, long max_frames, std::vector<int> *iters_log)
 {
-    ldpc_decoder *dec = Decoder.engine(fixpoint);
+    const int R = gpu_count();
+    std::vector<ldpc_decoder *> dec(R);
+    for (int r = 0; r < R; ++r) dec[r] = Decoder.engine_on(fixpoint, r);
     ldpc_mc_cfg cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.snr = snr; cfg.sigma = sigma;
@@ -74,29 +92,30 @@ Point simulate(FP_Decoder &Decoder, bool fixpoint, double snr, double sigma, con
     cfg.info_count = info_index ? (int)info_index->size() : 0;
     if (pins && !pins->empty()) { cfg.pin_index = &(*pins)[0]; cfg.pin_count = (int)pins->size(); cfg.pin_value = pin_value; }
 
-    Point pt = {0, 0, 0, 0};
-    size_t batch = 4096;  // grows: low-SNR points stop after a few hundred frames, high-SNR ones need millions
-    std::vector<uint16_t> ferr;
-    std::vector<int32_t> iters;
-    bool done = false;
-    while (!done) {
-        if (max_frames > 0 && (long)batch > max_frames - pt.Counter) batch = (size_t)(max_frames - pt.Counter);
-        ferr.resize(batch); iters.resize(batch);
-        cfg.first_frame = (uint64_t)pt.Counter;
-        int rc = ldpc_mc_run(dec, &cfg, batch, &ferr[0], &iters[0], NULL);
-        if (rc != LDPC_OK) ldpc_facade::fail("simulation launch", rc);
-        for (size_t i = 0; i < batch && !done; ++i) {
-            const double blkerror = rule == COUNT_ITERATIONS ? iters[i] : ferr[i];
-            if (blkerror > 0) pt.pckerror++;
-            pt.biterror += blkerror;
-            pt.iter_sum += iters[i];
-            pt.Counter++;
-            if (iters_log) iters_log->push_back(iters[i]);
-            if (stop_errors > 0 && pt.pckerror >= stop_errors) done = true;
-            if (max_frames > 0 && pt.Counter >= max_frames) done = true;
-        }
-        if (batch < (1u << 18)) batch *= 4;
+    ldpc_mc_stop stop;
+    memset(&stop, 0, sizeof stop);
+    stop.target_block_errors = stop_errors > 0 ? (uint64_t)stop_errors : 0;
+    stop.max_frames = max_frames > 0 ? (uint64_t)max_frames : 0;
+    stop.count_iterations = rule == COUNT_ITERATIONS;
+    const char *env = getenv("LDPC_MC_ROUND");
+    stop.frames_per_round = env && atol(env) > 0 ? (size_t)atol(env) : (size_t)1 << 15;
+    if (max_frames > 0 && (size_t)max_frames < stop.frames_per_round * R)
+        stop.frames_per_round = ((size_t)max_frames + R - 1) / R;
+    std::vector<int32_t> log;
+    if (iters_log) {
+        log.assign((size_t)1 << 22, 0);
+        stop.iters_out = &log[0];
+        stop.iters_cap = log.size();
     }
+    ldpc_mc_result res;
+    int rc = ldpc_mc_run_multi(&dec[0], R, &cfg, &stop, &res);
+    if (rc != LDPC_OK) ldpc_facade::fail("simulation", rc);
+    Point pt;
+    memset(&pt, 0, sizeof pt);
+    pt.biterror = (double)res.errors; pt.pckerror = (double)res.block_errors; pt.Counter = (long)res.frames;
+    pt.iter_sum = res.iter_sum; pt.devices = res.devices; pt.seconds = res.seconds;
+    for (int b = 0; b < 32; ++b) pt.iter_hist[b] = res.iter_hist[b];
+    if (iters_log) iters_log->assign(log.begin(), log.begin() + std::min<size_t>(log.size(), (size_t)res.frames));
     consume_uniforms((unsigned long long)pt.Counter * CWD_LENGTH);  // one uniform per transmitted bit (rvgs.cpp:169)
     return pt;
 }
@@ -282,11 +301,19 @@ int ArrayLDPC_Sweep(double db_start, double db_end, double db_step, const char *
     ofstream csv(Filename, std::ios::app);
     if (!csv) { std::cerr << "failed to open " << Filename << endl; return 1; }
     csv << "EbN0_dB,frames,frame_errors,bit_errors,FER,BER,avg_iters" << endl;
+    // the second file the reference opens and leaves empty (PerfTest.cpp:472-480): one line per point with the
+    // histogram of the decoder's return values (frames per iteration count 0..MAX_ITER), GPUs used and wall time
+    ofstream log((std::string(Filename) + "_log.txt").c_str(), std::ios::app);
     for (double db = db_start; db <= db_end + 1e-9; db += (db_step > 0 ? db_step : 1.0)) {
         double snr = 2 * pow(10.0, db / 10) * rate, sigma = sqrt(1 / snr);
         Point p = simulate(Decoder, fixpoint, snr, sigma, NULL, NULL, NULL, 0, COUNT_INFO_BIT_ERRORS, frame_errors, 0, NULL);
         csv << db << "," << p.Counter << "," << p.pckerror << "," << p.biterror << "," << p.pckerror / p.Counter << ","
             << p.biterror / p.Counter / CWD_LENGTH << "," << double(p.iter_sum) / p.Counter << endl;
+        if (log) {
+            log << "EbN0_dB " << db << " frames " << p.Counter << " gpus " << p.devices << " seconds " << p.seconds << " iterations";
+            for (int b = 0; b <= MAX_ITER; ++b) log << " " << p.iter_hist[b];
+            log << endl;
+        }
         cout << "Eb/N0 " << db << " dB: ";
         print_point(p);
     }

@@ -1026,6 +1026,8 @@ int ldpc_hard_decision_batch(ldpc_decoder *d, const int32_t *values, size_t fram
 }
 
 int ldpc_decoder_device(const ldpc_decoder *d) { return d ? d->device : LDPC_ERR_ARG; }
+const ldpc_code *ldpc_decoder_code(const ldpc_decoder *d) { return d ? &d->code : nullptr; }
+int ldpc_decoder_max_iter(const ldpc_decoder *d) { return d ? d->cfg.max_iter : LDPC_ERR_ARG; }
 
 int ldpc_decoder_sync(ldpc_decoder *d)
 {

@@ -451,14 +451,19 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32
 
 // shared-memory layout: [W][E] message words | [W][n] channel words | control block (16-byte aligned) | degree tables of
 // irregular codes | stage rows (16-byte aligned; the host passes the tables' size)
+// (offsets are added to the shared-memory base as plain pointer arithmetic -- the base itself is 16-byte aligned --
+// so that the compiler keeps the shared address space of everything derived from them: a round trip through an
+// integer turns every access to the control block into a generic one, and its shared atomics into global-style ATOMs)
 __device__ __forceinline__ Ctrl *ctrl_of(uint32_t *smem, int W, int E, int n)
 {
-    return reinterpret_cast<Ctrl *>((reinterpret_cast<uintptr_t>(smem + (size_t)W * (E + n)) + 15u) & ~(uintptr_t)15u);
+    const unsigned int words = ((unsigned int)W * (unsigned int)(E + n) + 3u) & ~3u;
+    return reinterpret_cast<Ctrl *>(smem + words);
 }
 __device__ __forceinline__ char *stage_of(uint32_t *smem, int W, int E, int n, const KParams &p)
 {
-    char *tables_end = reinterpret_cast<char *>(ctrl_of(smem, W, E, n) + 1) + p.tables_bytes;
-    return reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(tables_end) + 15u) & ~(uintptr_t)15u);
+    const unsigned int words = ((unsigned int)W * (unsigned int)(E + n) + 3u) & ~3u;
+    const unsigned int bytes = (words * 4u + (unsigned int)sizeof(Ctrl) + (unsigned int)p.tables_bytes + 15u) & ~15u;
+    return reinterpret_cast<char *>(smem) + bytes;
 }
 
 // ------------------------------------------------------------------------------------------

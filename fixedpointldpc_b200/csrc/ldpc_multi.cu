@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -44,9 +45,15 @@ static NcclApi *nccl_api()
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
+        // 1. the library LDPC_NCCL_LIB names (the Python binding points it at the NCCL PyTorch ships, so that a later
+        //    `import torch` in the same process finds the NCCL it was built against under the shared soname);
+        // 2. an NCCL the process has already loaded; 3. the system's.  Never RTLD_GLOBAL.
+        const char *env = getenv("LDPC_NCCL_LIB");
+        if (env && *env) api.handle = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+        if (!api.handle) api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
         for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
-            api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
             if (api.handle) break;
+            api.handle = dlopen(name, RTLD_NOW | RTLD_LOCAL);
         }
         if (!api.handle) return;
         api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(dlsym(api.handle, "ncclCommInitAll"));
@@ -143,7 +150,9 @@ extern "C" {
 void ldpc_mc_group_destroy(ldpc_mc_group *g)
 {
     if (!g) return;
-    ldpc::NcclApi *api = ldpc::nccl_api();
+    bool any_comm = false;
+    for (ncclComm_t c : g->comm) any_comm |= c != nullptr;
+    ldpc::NcclApi *api = any_comm ? ldpc::nccl_api() : nullptr;  // (a single-GPU group never touches NCCL)
     for (size_t r = 0; r < g->dec.size(); ++r) {
         cudaSetDevice(g->device[r]);
         if (r < g->comm.size() && g->comm[r] && api) api->CommDestroy(g->comm[r]);

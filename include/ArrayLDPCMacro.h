@@ -148,7 +148,28 @@ public:
         }
         return 0; /* IDLE etc.: the reference's loop body never runs and Iteration stays 0 */
     }
-    int decode_general(const double *) { return -1; }
+    /* ArrayLDPC_Decoder.cpp:735-933: the floating-point decoder (exact box-plus in FP64 on the GPU); fills Posteriori
+     * (getPost), DecodedCodeword and the double image of the edge memory (getEdgeDouble) */
+    int decode_general(const double *LLR)
+    {
+        ensure_decoder();
+        std::vector<uint32_t> bits((n_ + 31) / 32);
+        Posteriori.resize(n_); EdgeRAM.resize((size_t)dc_ * m_);
+        int iters = 0;
+        int rc = ldpc_decode_batch_f64(dec_gen, LLR, 1, &iters, &bits[0], &Posteriori[0], &EdgeRAM[0]);
+        if (rc != LDPC_OK) ldpc_facade::fail("FP_Decoder: decode_general failed", rc);
+        unpack(bits);
+        return iters;
+    }
+    double getPost(int Addr) { return Posteriori[Addr]; }
+    void wrtPost(int Addr, double in) { Posteriori[Addr] = in; }
+    double getEdgeDouble(int slot, int chk) { return EdgeRAM[(size_t)slot * m_ + chk]; } /* EdgeRAM[slot].BRAM[chk] */
+    /* ArrayLDPC_Decoder.cpp:724-732 */
+    double sxor(double x, double y)
+    {
+        double v1 = fabs(x), v2 = fabs(y), sum_abs = v1 + v2, diff_abs = fabs(v1 - v2);
+        return sgn(x) * sgn(y) * ((v2 < v1 ? v2 : v1) + log(1 + exp(-sum_abs)) - log(1 + exp(-diff_abs)));
+    }
 
     /* Batched extension: frames x CWD_LENGTH LLRs in, iteration counts out (bits optional, packed). */
     int decode_batch(const int *LLR, size_t frames, int *iters, uint32_t *bits, bool fixpoint)
@@ -229,6 +250,23 @@ public:
     int getInfoIndexAt(int i) { return InfoIndex[i]; }
     int getTrueInfoBit(int i) { return TrueInfoBit[i]; }
     ldpc_decoder *engine(bool fixpoint) { ensure_decoder(); return fixpoint ? dec_pre : dec_gen; }
+    /* one more decoder of the same code per additional GPU (multi-GPU frame loops of the drivers) */
+    ldpc_decoder *engine_on(bool fixpoint, int device)
+    {
+        if (device == 0) return engine(fixpoint);
+        ensure_decoder();
+        const size_t slot = (size_t)device * 2 + (fixpoint ? 1 : 0);
+        if (more_.size() <= slot) more_.resize(slot + 1, NULL);
+        if (!more_[slot]) {
+            ldpc_decoder_cfg cfg;
+            ldpc_decoder_cfg_default(&cfg);
+            cfg.max_iter = MAX_ITER; cfg.precheck = fixpoint ? 1 : 0; cfg.device = device;
+            int err = LDPC_OK;
+            more_[slot] = ldpc_decoder_create(code_, &cfg, &err);
+            if (!more_[slot]) ldpc_facade::fail("FP_Decoder: cannot create the GPU decoder", err);
+        }
+        return more_[slot];
+    }
     const ldpc_code *code() { return code_; }
 
 private:
@@ -273,6 +311,8 @@ private:
     {
         if (dec_gen) ldpc_decoder_destroy(dec_gen);
         if (dec_pre) ldpc_decoder_destroy(dec_pre);
+        for (size_t i = 0; i < more_.size(); i++) if (more_[i]) ldpc_decoder_destroy(more_[i]);
+        more_.clear();
         if (code_) ldpc_code_free(code_);
         dec_gen = dec_pre = NULL; code_ = NULL;
     }
@@ -335,9 +375,11 @@ private:
     class ControlFSM FSM;
     ldpc_code *code_;
     ldpc_decoder *dec_gen, *dec_pre;
+    std::vector<ldpc_decoder *> more_;
     int n_, m_, dc_;
     std::vector<int> DecodedCodeword, TrueCodeword, TrueInfoBit, InfoIndex, Posteriori_fp, EdgeRAM_fp;
     std::vector<int> post_tmp, edge_tmp;
+    std::vector<double> Posteriori, EdgeRAM;
     int BitError;
     int last_syndrome_fail;
     static const int Constant = int((5.0 / 8.0) * (1 << FRAC_WIDTH));

@@ -119,6 +119,16 @@ int ldpc_decode_batch(ldpc_decoder *dec, const int32_t *llr, size_t frames, int3
 int ldpc_decode_batch_i16(ldpc_decoder *dec, const int16_t *llr, size_t frames, int32_t *iters,
                           uint32_t *bits, int32_t *post, int32_t *v2c);
 
+/* Batched FP_Decoder::decode_general(const double *) (ArrayLDPC_Decoder.cpp:735-933): the reference's floating-point
+ * decoder with the exact box-plus sxor(double, double) (:724-732) and checkPost() (:335-372), in FP64 on the GPU.
+ *   llr [frames][n] double; iters / bits as above; post [frames][n] double (Posteriori); v2c [frames][dc_max][m]
+ *   double (EdgeRAM[slot].BRAM[check]).
+ * Same schedule and the same evaluation order of every sum as the reference; libm's log/exp differ from the host's
+ * by an ulp at most, so results agree with the reference to a relative 1e-9 on posteriors and messages and -- on
+ * all but marginal frames -- exactly in iteration counts and bits (tests/test_gpu_f64.py). */
+int ldpc_decode_batch_f64(ldpc_decoder *dec, const double *llr, size_t frames, int32_t *iters, uint32_t *bits,
+                          double *post, double *v2c);
+
 /* Same on DEVICE buffers, asynchronous on `stream` (a cudaStream_t, NULL = the decoder's own
  * stream).  llr_bits = 32 (int32) or 16 (int16) selects the input element type. */
 int ldpc_decode_batch_device(ldpc_decoder *dec, const void *d_llr, int llr_bits, size_t frames,
@@ -130,8 +140,10 @@ int ldpc_decode_batch_device(ldpc_decoder *dec, const void *d_llr, int llr_bits,
  * `values` are channel LLRs (hardDecision) or posteriors (checkPost*). */
 int ldpc_hard_decision_batch(ldpc_decoder *dec, const int32_t *values, size_t frames, int32_t *fail, uint32_t *bits);
 
-/* CUDA device ordinal the decoder is bound to. */
+/* CUDA device ordinal the decoder is bound to, its parity-check tables, its MAX_ITER. */
 int ldpc_decoder_device(const ldpc_decoder *dec);
+const ldpc_code *ldpc_decoder_code(const ldpc_decoder *dec);
+int ldpc_decoder_max_iter(const ldpc_decoder *dec);
 
 /* Blocks until everything queued on the decoder's streams has finished. */
 int ldpc_decoder_sync(ldpc_decoder *dec);

@@ -223,3 +223,80 @@ void oracle_encode(const oracle_gen *g, const char *in, int in_len, int *codewor
     }
     free(info);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * floating-point decoder (dead code in the reference's drivers, kept as the fixed-point loss yardstick)
+ * ------------------------------------------------------------------------------------------ */
+#define ORACLE_MAX_DEG 64
+static int sgn_d(double x) { return x > 0 ? 1 : -1; } /* ArrayLDPCMacro.h:218-221 */
+
+/* ArrayLDPC_Decoder.cpp:724-732 */
+double oracle_sxor_f64(double x, double y)
+{
+    double v1 = fabs(x), v2 = fabs(y);
+    double sum_abs = v1 + v2;
+    double diff_abs = fabs(v1 - v2);
+    double mn = v2 < v1 ? v2 : v1; /* std::min(v1, v2) */
+    return sgn_d(x) * sgn_d(y) * (mn + log(1 + exp(-sum_abs)) - log(1 + exp(-diff_abs)));
+}
+
+/* ArrayLDPC_Decoder.cpp:735-933 */
+int oracle_decode_general_f64(const oracle_code *code, const double *llr, int max_iter,
+                              int *bits, double *post, double *edge)
+{
+    const int n = code->n, m = code->m;
+    double fwd[ORACLE_MAX_DEG], bwd[ORACLE_MAX_DEG], mv[ORACLE_MAX_DEG];
+    int *addr_count = (int *)malloc(sizeof(int) * (size_t)m);
+    int it = 0, c, k, v, j;
+    /* :757-774 */
+    for (c = 0; c < m; c++)
+        for (k = 0; k < code->cdeg[c]; k++) edge[(size_t)k * m + c] = llr[code->clist[(size_t)c * code->dc_max + k]];
+    while (it < max_iter) {
+        /* check phase :779-833 */
+        for (c = 0; c < m; c++) {
+            const int d = code->cdeg[c];
+            for (k = 0; k < d; k++) mv[k] = edge[(size_t)k * m + c];
+            fwd[0] = mv[0];
+            bwd[d - 1] = mv[d - 1];
+            for (k = 1; k < d; k++) {
+                fwd[k] = oracle_sxor_f64(fwd[k - 1], mv[k]);
+                bwd[d - k - 1] = oracle_sxor_f64(bwd[d - k], mv[d - 1 - k]);
+            }
+            edge[c] = bwd[1];
+            edge[(size_t)(d - 1) * m + c] = fwd[d - 2];
+            for (k = 1; k < d - 1; k++) edge[(size_t)k * m + c] = oracle_sxor_f64(fwd[k - 1], bwd[k + 1]);
+        }
+        /* variable phase :835-872 */
+        memset(addr_count, 0, sizeof(int) * (size_t)m);
+        for (v = 0; v < n; v++) {
+            const int d = code->vdeg[v];
+            double accum = 0, mc[ORACLE_MAX_DEG];
+            for (j = 0; j < d; j++) {
+                const int chk = code->vlist[(size_t)v * code->dv_max + j];
+                mc[j] = edge[(size_t)addr_count[chk] * m + chk];
+                accum = accum + mc[j];
+            }
+            accum = accum + llr[v];
+            post[v] = accum;
+            for (j = 0; j < d; j++) {
+                const int chk = code->vlist[(size_t)v * code->dv_max + j];
+                edge[(size_t)addr_count[chk] * m + chk] = accum - mc[j];
+                addr_count[chk]++;
+            }
+        }
+        it++;
+        /* checkPost :335-372 */
+        {
+            int fail = 0;
+            for (v = 0; v < n; v++) bits[v] = post[v] > 0 ? 0 : 1;
+            for (c = 0; c < m && !fail; c++) {
+                int sum = 0;
+                for (k = 0; k < code->cdeg[c]; k++) sum ^= bits[code->clist[(size_t)c * code->dc_max + k]];
+                if (sum) fail = 1;
+            }
+            if (!fail) break;
+        }
+    }
+    free(addr_count);
+    return it;
+}

@@ -19,6 +19,7 @@ ORACLE_LIB = os.path.join(HERE, "_build", "liboracle.so")
 REF_DIR = os.path.join(HERE, "_ref")
 
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 
 
 class _Code(C.Structure):
@@ -156,10 +157,25 @@ class Oracle:
         L.oracle_set_info_bit.argtypes = [C.c_char_p, C.c_int, C.c_int, _i32p]
         L.oracle_calculate_ber.restype = C.c_int
         L.oracle_calculate_ber.argtypes = [_i32p, _i32p, _i32p, C.c_int]
+        L.oracle_sxor_f64.restype = C.c_double
+        L.oracle_sxor_f64.argtypes = [C.c_double, C.c_double]
+        L.oracle_decode_general_f64.restype = C.c_int
+        L.oracle_decode_general_f64.argtypes = [C.POINTER(_Code), _f64p, C.c_int, _i32p, _f64p, _f64p]
         self.seed = C.c_long(123456789)  # rngs.cpp:45 DEFAULT
 
     def sxor(self, x, y):
         return self.lib.oracle_sxor(int(x), int(y))
+
+    def sxor_f64(self, x, y):
+        return self.lib.oracle_sxor_f64(float(x), float(y))
+
+    def decode_f64(self, llr):
+        """decode_general(const double *): returns (iters, bits[n], post[n] float64, edge[dc_max][m] float64)."""
+        t = self.t
+        llr = np.ascontiguousarray(llr, dtype=np.float64)
+        bits, post, edge = np.zeros(t.n, np.int32), np.zeros(t.n, np.float64), np.zeros((t.dc_max, t.m), np.float64)
+        it = self.lib.oracle_decode_general_f64(C.byref(self._code), llr, self.max_iter, bits, post, edge.reshape(-1))
+        return it, bits, post, edge
 
     def decode(self, llr, precheck=False, state=None):
         """Returns (iters, bits[n], post[n], edge[dc_max][m]).  `state` = (bits, post, edge)
@@ -254,6 +270,11 @@ class Reference:
         L.ref_calculate_ber.restype = C.c_int
         L.ref_hard_decision.restype = C.c_int
         L.ref_hard_decision.argtypes = [_i32p]
+        if hasattr(L, "ref_decode_general"):
+            L.ref_decode_general.restype = C.c_int
+            L.ref_decode_general.argtypes = [_f64p, _i32p, _f64p, _f64p]
+            L.ref_sxor_f64.restype = C.c_double
+            L.ref_sxor_f64.argtypes = [C.c_double, C.c_double]
 
     def set_tables(self, t):
         assert (t.n, t.m) == (self.n, self.m) and t.dc_max <= self.dc and t.dv_max <= self.dv
@@ -283,6 +304,16 @@ class Reference:
         it = self.lib.ref_decode_fixpoint(np.ascontiguousarray(llr, np.int32), int(set_pcv), bits, post,
                                           edge.reshape(-1))
         return it, bits, post, edge
+
+    def decode_general(self, llr):
+        """FP_Decoder::decode_general(const double *): (iters, bits, post float64, edge float64 [dc][ram_depth])."""
+        bits, post = np.zeros(self.n, np.int32), np.zeros(self.n, np.float64)
+        edge = np.zeros((self.dc, self.ram_depth), np.float64)
+        it = self.lib.ref_decode_general(np.ascontiguousarray(llr, np.float64), bits, post, edge.reshape(-1))
+        return it, bits, post, edge
+
+    def sxor_f64(self, x, y):
+        return self.lib.ref_sxor_f64(float(x), float(y))
 
     def decode_many(self, llr, fixpoint):
         llr = np.ascontiguousarray(llr, np.int32).reshape(-1, self.n)

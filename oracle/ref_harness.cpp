@@ -117,6 +117,21 @@ int ref_decode_fixpoint(const int *llr, int set_pcv, int *bits, int *post, int *
     return it;
 }
 
+/* FP_Decoder::decode_general(const double *) (ArrayLDPC_Decoder.cpp:735-933); the double image of the edge memory is
+ * Memory::BRAM (ArrayLDPCMacro.h:102) */
+int ref_decode_general(const double *llr, int *bits, double *post, double *edge)
+{
+    FP_Decoder &d = dec();
+    int it = d.decode_general(llr);
+    if (bits) for (int v = 0; v < CWD_LENGTH; ++v) bits[v] = d.DecodedCodeword[v];
+    if (post) for (int v = 0; v < CWD_LENGTH; ++v) post[v] = d.Posteriori[v];
+    if (edge)
+        for (int k = 0; k < CHK_DEG; ++k)
+            for (int c = 0; c < RAM_DEPTH; ++c) edge[k * RAM_DEPTH + c] = d.EdgeRAM[k].BRAM[c];
+    return it;
+}
+double ref_sxor_f64(double x, double y) { return dec().sxor(x, y); }
+
 int ref_get_state(void) { return dec().getState(); }
 void ref_set_state(int s) { dec().setState(s); }
 int ref_sxor(int x, int y) { return dec().sxor(x, y); }

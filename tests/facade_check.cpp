@@ -1,6 +1,7 @@
 // facade_check.cpp -- drives the reference-compatible FP_Decoder class (include/ArrayLDPCMacro.h) exactly like
 // the reference's drivers do, one frame at a time, and compares every observable with vectors dumped from the
 // reference.  Built and run by tests/test_gpu_facade.py.   usage: facade_check <dir> <general|fixpoint>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +28,28 @@ int main(int argc, char **argv)
     if (argc < 3) return 2;
     const std::string dir = argv[1];
     const bool fixpoint = !strcmp(argv[2], "fixpoint");
+    if (!strcmp(argv[2], "double")) {
+        // FP_Decoder::decode_general(const double *) (ArrayLDPC_Decoder.cpp:735-933) through the facade, one frame at a
+        // time: return value and DecodedCodeword equal to the reference's, posteriors within the stated tolerance
+        std::vector<double> llr64 = slurp<double>(dir + "/llr64.bin"), post64 = slurp<double>(dir + "/post64.bin");
+        std::vector<int> it64 = slurp<int>(dir + "/iters.bin");
+        std::vector<unsigned char> b64 = slurp<unsigned char>(dir + "/bits.bin");
+        FP_Decoder D((dir + "/H.txt").c_str());
+        int wrong = 0;
+        for (size_t f = 0; f < it64.size(); f++) {
+            int it = D.decode_general(&llr64[f * CWD_LENGTH]);
+            if (it != it64[f]) { printf("frame %zu: iters %d want %d\n", f, it, it64[f]); wrong++; continue; }
+            const double rel = it < MAX_ITER ? 1e-9 : 1e-6;
+            for (int v = 0; v < CWD_LENGTH; v++) {
+                if (D.getDecodedBit(v) != b64[f * CWD_LENGTH + v]) { printf("frame %zu: bit %d\n", f, v); wrong++; break; }
+                const double want = post64[f * CWD_LENGTH + v], tol = rel * (fabs(want) > 1 ? fabs(want) : 1);
+                if (fabs(D.getPost(v) - want) > tol) { printf("frame %zu: post %d\n", f, v); wrong++; break; }
+            }
+        }
+        if (D.sxor(0.3, -2.0) >= 0 || fabs(D.sxor(5.0, 5.0) - (5.0 + log(1 + exp(-10.0)) - log(2.0))) > 1e-15) { printf("sxor(double)\n"); wrong++; }
+        printf("frames %zu zero_hits 0 mismatches %d\n", it64.size(), wrong);
+        return wrong ? 1 : 0;
+    }
     std::vector<int> llr = slurp<int>(dir + "/llr.bin"), iters = slurp<int>(dir + "/iters.bin"),
                      post = slurp<int>(dir + "/post.bin"), edge = slurp<int>(dir + "/edge.bin"),
                      cdeg = slurp<int>(dir + "/cdeg.bin");

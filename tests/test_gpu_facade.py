@@ -62,6 +62,23 @@ def test_fp_decoder_class_frame_by_frame(tmp_path, fp, golden, name, variant, mo
     assert "mismatches 0" in res.stdout
 
 
+@pytest.mark.parametrize("name,variant,tags", [("wifi", 0, ["wifi_2p0dB", "wifi_1p0dB"]), ("a5", 1, ["a5_4p5dB", "a5_3p0dB"])])
+def test_fp_decoder_class_floating_point_decoder(tmp_path, fp, name, variant, tags):
+    """decode_general(const double *) of the facade class against the reference's golden doubles."""
+    tmp = str(tmp_path)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_f64.npz"))
+    code = fp.codes.NAMED[name]()
+    code.save(os.path.join(tmp, "H.txt"))
+    np.concatenate([g[t + "_llr"] for t in tags]).astype(np.float64).tofile(os.path.join(tmp, "llr64.bin"))
+    np.concatenate([g[t + "_post"] for t in tags]).astype(np.float64).tofile(os.path.join(tmp, "post64.bin"))
+    np.concatenate([g[t + "_iters"] for t in tags]).astype(np.int32).tofile(os.path.join(tmp, "iters.bin"))
+    np.concatenate([np.unpackbits(g[t + "_bits"], axis=1)[:, :code.n] for t in tags]).astype(np.uint8).tofile(os.path.join(tmp, "bits.bin"))
+    exe = _build_check(tmp, variant)
+    res = subprocess.run([exe, tmp, "double"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "mismatches 0" in res.stdout
+
+
 def _wifi_files(tmp, fp, golden):
     code = fp.codes.wifi_1944_r12()
     code.save(os.path.join(tmp, "H_802.11_IndZero.txt"))
