@@ -45,7 +45,8 @@ class DecoderStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("frames", C.c_uint64), ("fallback_frames", C.c_uint64),
                 ("threads", C.c_int), ("threads32", C.c_int), ("frames_per_cta", C.c_int),
                 ("frames_per_cta32", C.c_int), ("grid", C.c_int), ("smem_bytes", C.c_int),
-                ("smem_bytes32", C.c_int), ("stage_rows", C.c_int)]
+                ("smem_bytes32", C.c_int), ("stage_rows", C.c_int),
+                ("resident_ctas_per_sm", C.c_int), ("launch_smem_bytes", C.c_int)]
 
 
 class McCfg(C.Structure):
@@ -112,17 +113,18 @@ def load_library():
     L.ldpc_mc_run.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp, vp, C.POINTER(McCounters)]
     L.ldpc_mc_run_device.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp, vp, vp, vp]
     L.ldpc_mc_channel.argtypes = [vp, C.POINTER(McCfg), C.c_size_t, vp]
-    L.ldpc_decoder_device.argtypes = [vp]
-    L.ldpc_decoder_code.restype = vp
-    L.ldpc_decoder_code.argtypes = [vp]
-    L.ldpc_decoder_max_iter.argtypes = [vp]
-    L.ldpc_decode_batch_f64.argtypes = [vp, vp, C.c_size_t, vp, vp, vp, vp]
-    L.ldpc_mc_group_create.restype = vp
-    L.ldpc_mc_group_create.argtypes = [C.POINTER(vp), C.c_int, ip]
-    L.ldpc_mc_group_size.argtypes = [vp]
-    L.ldpc_mc_group_run.argtypes = [vp, C.POINTER(McCfg), C.POINTER(McStop), C.POINTER(McResult)]
-    L.ldpc_mc_group_destroy.argtypes = [vp]
-    L.ldpc_mc_run_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(McCfg), C.POINTER(McStop), C.POINTER(McResult)]
+    if hasattr(L, "ldpc_mc_group_run"):  # (absent from older builds loaded through LDPC_B200_LIB for A/B runs)
+        L.ldpc_decoder_device.argtypes = [vp]
+        L.ldpc_decoder_code.restype = vp
+        L.ldpc_decoder_code.argtypes = [vp]
+        L.ldpc_decoder_max_iter.argtypes = [vp]
+        L.ldpc_decode_batch_f64.argtypes = [vp, vp, C.c_size_t, vp, vp, vp, vp]
+        L.ldpc_mc_group_create.restype = vp
+        L.ldpc_mc_group_create.argtypes = [C.POINTER(vp), C.c_int, ip]
+        L.ldpc_mc_group_size.argtypes = [vp]
+        L.ldpc_mc_group_run.argtypes = [vp, C.POINTER(McCfg), C.POINTER(McStop), C.POINTER(McResult)]
+        L.ldpc_mc_group_destroy.argtypes = [vp]
+        L.ldpc_mc_run_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(McCfg), C.POINTER(McStop), C.POINTER(McResult)]
     L.ldpc_hard_decision_batch.argtypes = [vp, vp, C.c_size_t, vp, vp]
     L.ldpc_gen_load.restype = vp
     L.ldpc_gen_load.argtypes = [C.c_char_p, ip]

@@ -363,6 +363,12 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     d.stats.kernel_launches++;
     d.stats.grid = grid;
     d.stats.stage_rows = p.stage_rows;
+    if (which == 0 || d.cfg.precision == 32) {
+        int resident = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, (const void *)pl.kernel.fn, pl.threads, smem) == cudaSuccess)
+            d.stats.resident_ctas_per_sm = resident;
+        d.stats.launch_smem_bytes = smem;
+    }
     return LDPC_OK;
 }
 

@@ -423,6 +423,7 @@ struct Ctrl {
     int ntake;          // entries taken from the queue of claimed frames
     int drained;        // per-slot claims: the global queue is exhausted
     unsigned long long claim;  // first of the `ntake` queue positions claimed to replace them
+    unsigned int dbg_frames;   // frames this CTA took (phase-timing builds print it)
 };
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ------------------------------------------
@@ -1023,7 +1024,7 @@ __device__ __forceinline__ Source planner_next(const KParams &p, const Ctrl *ctr
 // decision (ctrl->active itself is rewritten by the header update: every thread reads it here), and ends with the
 // barrier behind which the variable phase may run.  Returns the slots that hold a frame after the pass.
 template <class T>
-__device__ __noinline__ uint32_t refill_pass(const KParams &p, uint32_t *smem, uint32_t want, bool sync, int n, int E, int W,
+__device__ __forceinline__ uint32_t refill_pass(const KParams &p, uint32_t *smem, uint32_t want, bool sync, int n, int E, int W,
                                              unsigned int trip, int buf)
 {
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -1176,7 +1177,7 @@ __device__ __noinline__ uint32_t refill_pass(const KParams &p, uint32_t *smem, u
 //                values of the first `stage_rows` entries into their stage rows, the fed launch's arrival mark
 //   warp 0       L2 prefetch of the channel values the refill will read from global memory
 template <class T>
-__device__ __noinline__ void header_update(const KParams &p, uint32_t *smem, bool sync, int n, int E, int W, unsigned int trip, int rbuf)
+__device__ __forceinline__ void header_update(const KParams &p, uint32_t *smem, bool sync, int n, int E, int W, unsigned int trip, int rbuf)
 {
     const int tid = threadIdx.x, lane_id = tid & 31;
     const int nslots = W * T::LANES;
@@ -1213,6 +1214,9 @@ __device__ __noinline__ void header_update(const KParams &p, uint32_t *smem, boo
             }
         }
         ctrl->errs[s] = 0u;
+#ifdef LDPC_PHASE_TIMING
+        if ((taken >> s) & 1u) atomicAdd(&ctrl->dbg_frames, 1u);
+#endif
         ctrl->fid[s] = ((taken >> s) & 1u) ? ctrl->newfid[s] : -1;
         ctrl->start[s] = trip;  // its first (initialising) variable phase runs in this trip
     }
@@ -1355,6 +1359,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
     if (tid < MAX_FIFO) { ctrl->q_fid[tid] = -1; ctrl->q_par[tid] = 0; }
     if (tid == 0) {
         ctrl->q_head = 0u; ctrl->q_staged = 0u; ctrl->avail = 0;
+        ctrl->dbg_frames = 0u;
         ctrl->active = 0u; ctrl->served = 0u; ctrl->report = 0u; ctrl->taken = 0u; ctrl->ntake = 0; ctrl->drained = 0; ctrl->claim = 0ull;
         for (int r = 0; r < MAX_STAGE; ++r) { mbar_init(&ctrl->bar[r], 1u); ctrl->row_uses[r] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1364,6 +1369,8 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
     const int items = (W / NI) * m;  // (word-set group, check)
 #ifdef LDPC_PHASE_TIMING
     long long t_phase[4] = {0, 0, 0, 0}, t_mark = clock64();
+    long long t_start;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 #define LDPC_MARK(k) do { long long t_now = clock64(); t_phase[k] += t_now - t_mark; t_mark = t_now; } while (0)
 #else
 #define LDPC_MARK(k) do { } while (0)
@@ -1396,7 +1403,8 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
         buf = buf == 2 ? 0 : buf + 1;
         LDPC_MARK(0);
         if (p.post || p.v2c) {
-            if (ctrl->served) {  // the parity-mode variable phase looks up the frame of every lane
+            if (want) {  // the parity-mode variable phase looks up the frame of every lane (`want`, not ctrl->served:
+                         // thread 0 rewrote that word after the last barrier)
                 header_update<T>(p, smem, sync, n, E, W, trip, rbuf);
                 __syncthreads();
             }
@@ -1417,9 +1425,9 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
         LDPC_MARK(3);
     }
 #ifdef LDPC_PHASE_TIMING
-    if (tid == 0 && blockIdx.x == 0 && trip > 0)
-        printf("phase cycles (CTA 0): results+refill %lld variable %lld check %lld stop decision %lld | trips %u\n", t_phase[0],
-               t_phase[1], t_phase[2], t_phase[3], trip);
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 1 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1) && trip > 0)
+        printf("phase cycles (CTA %d): results+refill %lld variable %lld check %lld stop decision %lld | trips %u frames %u t0 %lld\n",
+               (int)blockIdx.x, t_phase[0], t_phase[1], t_phase[2], t_phase[3], trip, ctrl->dbg_frames, t_start);
 #endif
 }
 

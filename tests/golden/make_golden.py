@@ -153,6 +153,16 @@ def main():
         out = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "wrapper_a5"), "2", "2", "1", "t.csv"], cwd=tmp,
                              capture_output=True, text=True).stdout
         lines.append("# wrapper_a5 a b c d  -> ArrayLDPC_PerfTest(2,2,1,\"test.csv\") (Wrapper.cpp:27)\n" + out)
+    # the drivers the reference's own main leaves unreachable, through the dispatching main of
+    # oracle/ref_driver_main.cpp: ArrayLDPC_Debug_Shorten (PerfTest.cpp:318-431, prints every return value),
+    # ArrayLDPC_Debug (:217-316), ArrayLDPC_TimeTrial (:520-607)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.symlink(os.path.join(REF, "codes", "G_array_forward.txt"), os.path.join(tmp, "G_array_forward.txt"))
+        with open(os.path.join(OUT, "reference_drivers.txt"), "w") as fh:
+            for args in ("shorten 36", "shorten 200", "debug", "timetrial 2 300", "timetrial 6 500"):
+                out = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "wrapper_a5")] + args.split(), cwd=tmp,
+                                     capture_output=True, text=True).stdout
+                fh.write("# wrapper_a5 %s\n" % args + out)
     if "--transcript" in sys.argv:
         with tempfile.TemporaryDirectory() as tmp:
             for f in ("H_802.11_IndZero.txt", "H_802.11_IndZerog.txt"):
