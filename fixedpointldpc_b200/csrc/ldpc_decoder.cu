@@ -35,10 +35,12 @@ struct KernelChoice {
     bool cdeg_in_smem = false, vdeg_in_smem = false;
 };
 
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA = 0, int ARRP = 0> static KernelChoice make_choice()
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA = 0, int ARRP = 0, unsigned VMASK = 0xffffffffu,
+          unsigned CMASK = 0xffffffffu>
+static KernelChoice make_choice()
 {
     KernelChoice k;
-    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA, ARRP>;
+    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA, ARRP, VMASK, CMASK>;
     k.max_threads = MAXT;
     k.ni = NI;
     k.ctas_per_sm = NCTA;
@@ -94,8 +96,14 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
         return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212>();
     int full = 0, last = 0;  // words per word set with the checks sorted by descending degree (see ldpc_decoder::e_words)
     for (int d : c.cdeg) { full += (d >= c.dc_max - 1); last += (d == c.dc_max); }
-    if (c.dc_max == 8 && c.dv_max <= 12 && c.m == 972 && c.n == 1944 && full == 972 && last == 162)  // 802.11n 1944 r1/2
+    if (c.dc_max == 8 && c.dv_max <= 12 && c.m == 972 && c.n == 1944 && full == 972 && last == 162) {  // 802.11n 1944 r1/2
+        // exact bodies only for the degrees the code has (variables 2, 3, 4, 11; checks 7, 8): a third of the code size
+        bool only = true;
+        for (int d : c.vdeg) only &= (d == 2 || d == 3 || d == 4 || d == 11);
+        if (only && !getenv("LDPC_WIFI_ALL_DEGREES"))
+            return make_choice<T, 8, false, 12, 3, 512, 2, 972, 1944, 7 * 972 + 162, 0, (1u << 2) | (1u << 3) | (1u << 4) | (1u << 11), (1u << 7) | (1u << 8)>();
         return make_choice<T, 8, false, 12, 3, 512, 2, 972, 1944, 7 * 972 + 162>();  // three word sets per CTA and thread
+    }
     // any other code: run-time dimensions
     if (regular && c.dc_max == 47 && c.dv_max <= 5) return make_choice<T, 47, true, 5, 1, 256, 4, 0, 0>();
     if (c.dc_max <= 8 && c.dv_max <= 12) return make_choice<T, 8, false, 12, 2, 512, 2, 0, 0>();

@@ -410,6 +410,8 @@ struct Ctrl {
     // second one -- so all threads see the same queue when they plan a refill.
     int q_fid[MAX_FIFO];
     unsigned char q_par[MAX_FIFO];      // staged entries: phase parity of their row's mbarrier for this use
+    unsigned char q_row[MAX_FIFO];      // staged entries: their stage row
+    unsigned int q_head_idx;            // q_head % fifo_depth (kept so that nobody but thread 0 divides)
     unsigned char row_uses[MAX_STAGE];  // bulk copies issued into each row so far (mod 256)
     unsigned int q_head, q_staged;
     long long avail;                    // frames [0, avail) have arrived (fed launches; otherwise all)
@@ -567,7 +569,9 @@ __device__ __forceinline__ uint32_t check_node_any(uint32_t *e, int m, int d)
 }
 
 // thread per (word-set group, check); the syndrome bits are OR-ed into fail[word set], one shared atomic per warp
-template <class T, int DC, bool REG, int NI>
+// CMASK: check degrees that get an exact body (bit d); a named irregular code lists its own, which keeps the hot
+// code small (the 802.11 code has degrees 7 and 8 only -- fifteen exact bodies would be 5 000 instructions)
+template <class T, int DC, bool REG, int NI, unsigned CMASK>
 __device__ __forceinline__ void check_phase(const KParams &p, uint32_t *fail, uint32_t *edge, const uint8_t *cdeg_s,
                                             int items, int m, int E, int W)
 {
@@ -592,7 +596,7 @@ __device__ __forceinline__ void check_phase(const KParams &p, uint32_t *fail, ui
                 if (DC <= 16) {
                     // exact-degree bodies: no per-edge predicates or branches inside
                     switch (d) {
-#define LDPC_CCASE(D) case D: if (D <= DC) { check_nodes<T, (D <= DC ? D : 2), NI>(e0, m, E, fb); done = true; } break;
+#define LDPC_CCASE(D) case D: if (D <= DC && ((CMASK >> D) & 1u)) { check_nodes<T, (D <= DC ? D : 2), NI>(e0, m, E, fb); done = true; } break;
                         LDPC_CCASE(2) LDPC_CCASE(3) LDPC_CCASE(4) LDPC_CCASE(5) LDPC_CCASE(6) LDPC_CCASE(7) LDPC_CCASE(8)
                         LDPC_CCASE(9) LDPC_CCASE(10) LDPC_CCASE(11) LDPC_CCASE(12) LDPC_CCASE(13) LDPC_CCASE(14)
                         LDPC_CCASE(15) LDPC_CCASE(16)
@@ -804,7 +808,8 @@ __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, 
 
 // REGV: every variable has degree DV -- the edge addresses of the thread's next variable are fetched while the
 // current one is processed (the table lives in global memory / L2)
-template <class T, int DV, bool PARITY, bool REGV>
+// VMASK: variable degrees that get an exact body (bit d), see CMASK
+template <class T, int DV, bool PARITY, bool REGV, unsigned VMASK>
 __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
                                                int n, int E, const uint8_t *vdeg)
 {
@@ -836,7 +841,7 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
             if (DV <= 12) {
                 // exact-degree bodies: no per-edge predicates or branches inside
                 switch (dv) {
-#define LDPC_VCASE(D) case D: if (D <= DV) { variable_node<T, (D <= DV ? D : 1), PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E); done = true; } break;
+#define LDPC_VCASE(D) case D: if (D <= DV && ((VMASK >> D) & 1u)) { variable_node<T, (D <= DV ? D : 1), PARITY>(p, ctrl, gflag, edge, llr, v, W, n, E); done = true; } break;
                     LDPC_VCASE(0) LDPC_VCASE(1) LDPC_VCASE(2) LDPC_VCASE(3) LDPC_VCASE(4) LDPC_VCASE(5) LDPC_VCASE(6)
                     LDPC_VCASE(7) LDPC_VCASE(8) LDPC_VCASE(9) LDPC_VCASE(10) LDPC_VCASE(11) LDPC_VCASE(12)
 #undef LDPC_VCASE
@@ -882,12 +887,12 @@ __device__ __forceinline__ void variable_phase_array(const KParams &p, Ctrl *ctr
 
 // parity-mode variant (posteriors and messages written through every iteration): kept out of line so that its
 // register needs do not shape the allocation of the throughput path
-template <class T, int DV, bool REGV, int ARRP>
+template <class T, int DV, bool REGV, int ARRP, unsigned VMASK>
 __device__ __noinline__ void variable_phase_parity(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
                                                    int n, int m, int E, const uint8_t *vdeg)
 {
     if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), true>(p, ctrl, gflag, edge, llr, W, n, m, E);
-    else variable_phase<T, DV, true, REGV>(p, ctrl, gflag, edge, llr, W, n, E, vdeg);
+    else variable_phase<T, DV, true, REGV, VMASK>(p, ctrl, gflag, edge, llr, W, n, E, vdeg);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -993,25 +998,27 @@ struct Source {
     uint32_t parity;
 };
 struct Planner {
-    unsigned int head, staged;
+    unsigned int head, head_idx, staged;
     long long avail;
     int taken;
     bool blocked;
 };
 __device__ __forceinline__ Planner planner_init(const Ctrl *ctrl)
 {
-    return Planner{ctrl->q_head, ctrl->q_staged, ctrl->avail, 0, false};
+    return Planner{ctrl->q_head, ctrl->q_head_idx, ctrl->q_staged, ctrl->avail, 0, false};
 }
 __device__ __forceinline__ Source planner_next(const KParams &p, const Ctrl *ctrl, Planner &pl, int s, bool sync)
 {
     if (sync) return Source{ctrl->newfid[s], -1, 0u};
     if (pl.blocked || pl.taken >= p.fifo_depth) { pl.blocked = true; return Source{-1, -1, 0u}; }
     const unsigned int e = pl.head + (unsigned int)pl.taken;
-    const int f = ctrl->q_fid[e % (unsigned int)p.fifo_depth];
+    unsigned int idx = pl.head_idx + (unsigned int)pl.taken;  // e % fifo_depth
+    if (idx >= (unsigned int)p.fifo_depth) idx -= (unsigned int)p.fifo_depth;
+    const int f = ctrl->q_fid[idx];
     if (f < 0) { pl.blocked = true; return Source{-1, -1, 0u}; }
     if (e < pl.staged) {
         ++pl.taken;
-        return Source{f, (int)(e % (unsigned int)p.stage_rows), (uint32_t)ctrl->q_par[e % (unsigned int)p.fifo_depth]};
+        return Source{f, (int)ctrl->q_row[idx], (uint32_t)ctrl->q_par[idx]};
     }
     if (p.mc_mode == 0 && (long long)f >= pl.avail) { pl.blocked = true; return Source{-1, -1, 0u}; }
     ++pl.taken;
@@ -1234,6 +1241,7 @@ __device__ __forceinline__ void header_update(const KParams &p, uint32_t *smem, 
                 ctrl->q_fid[(head + L + (unsigned int)k) % L] = queue_frame(p, claim + (unsigned long long)k, frames);
             head += (unsigned int)ntake;
             ctrl->q_head = head;
+            ctrl->q_head_idx = head % L;
         }
         const long long avail = frames_arrived(p, frames);
         ctrl->avail = avail;
@@ -1249,6 +1257,7 @@ __device__ __forceinline__ void header_update(const KParams &p, uint32_t *smem, 
                 const uintptr_t lo = first & ~(uintptr_t)15u;
                 const uint32_t len = (uint32_t)(((first + bytes + 15u) & ~(uintptr_t)15u) - lo);
                 unsigned long long *bar = &ctrl->bar[staged % S];
+                ctrl->q_row[staged % L] = (unsigned char)(staged % S);
                 ctrl->q_par[staged % L] = ctrl->row_uses[staged % S] & 1u;  // a row is skipped when its entry is read directly
                 ctrl->row_uses[staged % S]++;
                 mbar_expect_tx(bar, len);
@@ -1293,7 +1302,7 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
             const bool over = (ctrl->gflag[buf][w] >> lane) & 1u;
             stop = it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over;
         } else if (fifo) {
-            stop = ctrl->q_fid[ctrl->q_head % (unsigned int)p.fifo_depth] >= 0;
+            stop = ctrl->q_fid[ctrl->q_head_idx] >= 0;
         } else {
             stop = !ctrl->drained;  // short queue: idle slots claim for themselves while frames are left
         }
@@ -1317,6 +1326,7 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
 //   M, N compile-time m and n of the named codes (0 = read them from the parameters); EA: words per word set if
 //        that is less than DC*M (irregular named code)
 //   ARRP forward square array code with this circulant size: edge addresses in closed form (variable_phase_array)
+//   VMASK, CMASK  irregular codes: the variable / check degrees that get exact bodies (all ones: every degree up to DV / DC)
 //   MAXT, NCTA  launch bounds: CTA size and co-resident CTAs per SM.  Co-resident CTAs drift out of phase, so
 //        one's latency-bound variable phase overlaps the other's ALU-bound check phase.
 //
@@ -1330,7 +1340,7 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
 // so a frame that stops costs one check phase more than the reference executes, and a converged frame is
 // found by the same two barriers per trip that the phases need anyway.
 // ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA, int ARRP>
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA, int ARRP, unsigned VMASK, unsigned CMASK>
 __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constant__ KParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -1356,9 +1366,9 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
     if (tid < MAX_SLOTS) {
         ctrl->fid[tid] = -1; ctrl->start[tid] = 0u; ctrl->newfid[tid] = -1; ctrl->errs[tid] = 0u; ctrl->lehmer[tid] = 0u;
     }
-    if (tid < MAX_FIFO) { ctrl->q_fid[tid] = -1; ctrl->q_par[tid] = 0; }
+    if (tid < MAX_FIFO) { ctrl->q_fid[tid] = -1; ctrl->q_par[tid] = 0; ctrl->q_row[tid] = 0; }
     if (tid == 0) {
-        ctrl->q_head = 0u; ctrl->q_staged = 0u; ctrl->avail = 0;
+        ctrl->q_head = 0u; ctrl->q_head_idx = 0u; ctrl->q_staged = 0u; ctrl->avail = 0;
         ctrl->dbg_frames = 0u;
         ctrl->active = 0u; ctrl->served = 0u; ctrl->report = 0u; ctrl->taken = 0u; ctrl->ntake = 0; ctrl->drained = 0; ctrl->claim = 0ull;
         for (int r = 0; r < MAX_STAGE; ++r) { mbar_init(&ctrl->bar[r], 1u); ctrl->row_uses[r] = 0; }
@@ -1391,7 +1401,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
             // frames have not arrived yet) look again
             if (want || p.claim_ahead) header_update<T>(p, smem, sync, n, E, W, trip, buf);
             __syncthreads();
-            const bool more = p.claim_ahead ? ctrl->q_fid[ctrl->q_head % (unsigned int)p.fifo_depth] >= 0 : !ctrl->drained;
+            const bool more = p.claim_ahead ? ctrl->q_fid[ctrl->q_head_idx] >= 0 : !ctrl->drained;
             if (!more) break;
             __syncthreads();  // q_* were read above; thread 0 rewrites them in the next header update
             __nanosleep(500);
@@ -1408,16 +1418,16 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
                 header_update<T>(p, smem, sync, n, E, W, trip, rbuf);
                 __syncthreads();
             }
-            variable_phase_parity<T, DV, REGV, ARRP>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s);
+            variable_phase_parity<T, DV, REGV, ARRP, VMASK>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s);
         } else if (ARRP) {
             variable_phase_array<T, DV, (ARRP ? ARRP : 1), false>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E);
         } else {
-            variable_phase<T, DV, false, REGV>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s);
+            variable_phase<T, DV, false, REGV, VMASK>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s);
         }
         __syncthreads();
         LDPC_MARK(1);
         if (ctrl->served && !(p.post || p.v2c)) header_update<T>(p, smem, sync, n, E, W, trip, rbuf);
-        check_phase<T, DC, REG, NI>(p, ctrl->fail[buf], edge, cdeg_s, items, m, E, W);
+        check_phase<T, DC, REG, NI, CMASK>(p, ctrl->fail[buf], edge, cdeg_s, items, m, E, W);
         __syncthreads();
         LDPC_MARK(2);
         want = stop_decision<T>(p, ctrl, W, p.claim_ahead != 0, trip, buf);

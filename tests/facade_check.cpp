@@ -1,6 +1,7 @@
 // facade_check.cpp -- drives the reference-compatible FP_Decoder class (include/ArrayLDPCMacro.h) exactly like
 // the reference's drivers do, one frame at a time, and compares every observable with vectors dumped from the
 // reference.  Built and run by tests/test_gpu_facade.py.   usage: facade_check <dir> <general|fixpoint>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +29,26 @@ int main(int argc, char **argv)
     if (argc < 3) return 2;
     const std::string dir = argv[1];
     const bool fixpoint = !strcmp(argv[2], "fixpoint");
+    if (!strcmp(argv[2], "latency")) {
+        // one frame per call, like the reference's drivers: wall time per call of the facade's decode entry points
+        std::vector<int> llr = slurp<int>(dir + "/llr.bin"), it0 = slurp<int>(dir + "/iters.bin");
+        FP_Decoder D((dir + "/H.txt").c_str());
+        const int frames = (int)it0.size(), reps = 50;
+        D.decode_general_fp(&llr[0]);  // device set-up
+        for (int mode = 0; mode < 2; mode++) {
+            long total_it = 0;
+            auto t0 = std::chrono::steady_clock::now();
+            for (int r = 0; r < reps; r++)
+                for (int f = 0; f < frames; f++) {
+                    if (mode) { D.setState(PCV); total_it += D.decode_fixpoint(&llr[(size_t)f * CWD_LENGTH]); }
+                    else total_it += D.decode_general_fp(&llr[(size_t)f * CWD_LENGTH]);
+                }
+            double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / (reps * frames);
+            printf("%s: %.1f us per call (%d calls, %.2f iterations on average)\n", mode ? "decode_fixpoint" : "decode_general_fp", us,
+                   reps * frames, double(total_it) / (reps * frames));
+        }
+        return 0;
+    }
     if (!strcmp(argv[2], "double")) {
         // FP_Decoder::decode_general(const double *) (ArrayLDPC_Decoder.cpp:735-933) through the facade, one frame at a
         // time: return value and DecodedCodeword equal to the reference's, posteriors within the stated tolerance

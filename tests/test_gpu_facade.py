@@ -79,6 +79,23 @@ def test_fp_decoder_class_floating_point_decoder(tmp_path, fp, name, variant, ta
     assert "mismatches 0" in res.stdout
 
 
+def test_facade_per_frame_latency(tmp_path, fp, golden):
+    """The reference's drivers decode one frame per call; this is what such a caller pays per call through the facade
+    (one engine call for decode_fixpoint: pre-check and decode in the same launch).  Recorded, bounded loosely."""
+    tmp = str(tmp_path)
+    _dump_case(tmp, fp, golden, "a5", ["a5_4p5dB"])
+    exe = _build_check(tmp, 1)
+    res = subprocess.run([exe, tmp, "latency"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    print(res.stdout)
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "facade_latency.txt"), "w") as fh:
+            fh.write(res.stdout)
+    us = [float(l.split(":")[1].split()[0]) for l in res.stdout.strip().split("\n")]
+    assert len(us) == 2 and max(us) < 5000.0
+
+
 def _wifi_files(tmp, fp, golden):
     code = fp.codes.wifi_1944_r12()
     code.save(os.path.join(tmp, "H_802.11_IndZero.txt"))
