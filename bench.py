@@ -377,7 +377,7 @@ def bench_code(ctx, code_name, steps, warmup, headline):
         "avg_iters": avg_iters, "config": workload_config(code_name),
         "run": {"frames_per_step_per_gpu": frames, "fallback_frames": fallback, "precision": args.precision,
                 "threads": dec.stats()["threads"], "frames_per_cta": dec.stats()["frames_per_cta"], "grid": dec.stats()["grid"],
-                "stage_rows": dec.stats()["stage_rows"], "resident_ctas_per_sm": dec.stats()["resident_ctas_per_sm"],
+                "resident_ctas_per_sm": dec.stats()["resident_ctas_per_sm"],
                 "launch_smem_bytes": dec.stats()["launch_smem_bytes"]},
         "operating_point": {"ebn0_db": ebn0_op, "avg_iters": it_op, "value": world * frames / (ms_op * 1e-3) * k / 1e9,
                             "unit": "Gbit/s", "frames_per_s": world * frames / (ms_op * 1e-3),

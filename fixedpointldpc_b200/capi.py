@@ -45,7 +45,7 @@ class DecoderStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("frames", C.c_uint64), ("fallback_frames", C.c_uint64),
                 ("threads", C.c_int), ("threads32", C.c_int), ("frames_per_cta", C.c_int),
                 ("frames_per_cta32", C.c_int), ("grid", C.c_int), ("smem_bytes", C.c_int),
-                ("smem_bytes32", C.c_int), ("stage_rows", C.c_int),
+                ("smem_bytes32", C.c_int),
                 ("resident_ctas_per_sm", C.c_int), ("launch_smem_bytes", C.c_int)]
 
 

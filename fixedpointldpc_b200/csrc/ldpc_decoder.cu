@@ -83,14 +83,18 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
     // half the unrolled code, four independent phase streams per SM); the short 802.11 checks prefer interleaved
     // chains, and with the compact word sets three of them fit a CTA (NI = 3: +5 % over NI = 2).
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 5 && c.m == 235 && c.n == 2209) {        // array p47 r5
-        if (getenv("LDPC_A5_CLOSED") && is_forward_array(c, 47)) return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209, 0, 47>();
+        // closed-form edge addresses measured +1 % at 30 iterations, +2 % at the operating point over the table with
+        // its one-variable prefetch (profiles/r02/launch_shape_sweep.txt); LDPC_A5_TABLE=1 keeps the table
+        if (!getenv("LDPC_A5_TABLE") && is_forward_array(c, 47)) return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209, 0, 47>();
         return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209>();
     }
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 24 && c.m == 1128 && c.n == 2209 && is_forward_array(c, 47))  // array p47 r24
     {
-        // 576 and 640 threads get the same 96 registers; 512 threads get 128 (no spills in the chains)
-        if (getenv("LDPC_A24_512")) return make_choice<T, 47, true, 24, 1, 512, 1, 1128, 2209, 0, 47>();
-        return make_choice<T, 47, true, 24, 1, 640, 1, 1128, 2209, 0, 47>();
+        // One 221 KB word set per SM.  A 512-thread bound gives the chains 128 registers (no spills); make_plan then
+        // picks 384 threads: 12 warps x 3 passes cover the 36 warp-loads of checks exactly, three warps per scheduler
+        // (0.60 M frames/s against 0.53 M for 576 threads / 96 registers, 0.58 M for 640).  LDPC_A24_640=1: the 96-register build.
+        if (getenv("LDPC_A24_640")) return make_choice<T, 47, true, 24, 1, 640, 1, 1128, 2209, 0, 47>();
+        return make_choice<T, 47, true, 24, 1, 512, 1, 1128, 2209, 0, 47>();
     }
     if (regular && vregular && c.dc_max == 28 && c.dv_max == 4 && c.m == 316 && c.n == 2212)          // cut79
         return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212>();
@@ -113,8 +117,7 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
 
 struct Plan {
     KernelChoice kernel;
-    int W = 0, threads = 0, smem = 0;  // smem: word sets + control block + tables (stage rows come on top, per launch)
-    int smem_limit = 0;                // what one CTA may use with this many co-resident CTAs
+    int W = 0, threads = 0, smem = 0;  // smem: word sets + control block + degree tables
     // irregular codes: which variable / check every thread handles in pass k of the variable / check phase
     // ([k][thread], 0xffff = none), see build_order()
     uint16_t *d_vorder = nullptr, *d_corder = nullptr;
@@ -207,8 +210,7 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
     }
     if (want_threads > 0) best_t = std::min(k.max_threads, std::max(32, (want_threads / 32) * 32));
     out.kernel = k; out.W = W; out.threads = best_t;
-    out.smem = W * per_w + 16 + (int)sizeof(Ctrl) + tables + 16;  // the control block and the stage rows are 16-byte aligned
-    out.smem_limit = limit;
+    out.smem = W * per_w + (int)sizeof(Ctrl) + tables;
     // the attribute belongs to the kernel instantiation, not to this decoder: decoders that share an instantiation
     // with different word-set counts would otherwise lower each other's limit
     cudaError_t e = cudaFuncSetAttribute((const void *)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem);
@@ -355,22 +357,12 @@ static int launch(ldpc_decoder &d, const Plan &pl, int which, const void *llr, i
     // indirect queue (re-decode list) is only known on the device.
     p.claim_ahead = (!count && frames >= 4 * slots * grid) ? 1 : 0;
     if (fed) { p.claim_ahead = 1; p.avail = fed->avail; p.done_count = fed->done_count; p.done_flag = fed->done_flag; p.done_chunk = fed->done_chunk; }
-    // The CTA keeps as many frames claimed ahead as it has slots, and the channel values of the first of them travel
-    // into stage rows in shared memory by TMA bulk copies while the CTA decodes (16-bit values from memory only; as
-    // many rows as the shared memory left over holds).
-    p.fifo_depth = (int)std::min<long long>(slots, MAX_FIFO);
-    p.stage_stride = ((c.n * 2 + 32) + 15) & ~15;
-    p.stage_rows = 0;
-    if (p.claim_ahead && !mc && llr_bits == 16 && !getenv("LDPC_NO_STAGE"))
-        p.stage_rows = std::max(0, std::min({(pl.smem_limit - pl.smem) / p.stage_stride, (int)MAX_STAGE, p.fifo_depth}));
-    p.tables_bytes = (pl.kernel.cdeg_in_smem ? ((c.m + 15) & ~15) : 0) + (pl.kernel.vdeg_in_smem ? ((c.n + 15) & ~15) : 0);
-    const int smem = pl.smem + p.stage_rows * p.stage_stride;
+    const int smem = pl.smem;
     CUDA_TRY(cudaMemsetAsync(p.queue, 0, sizeof(unsigned long long), st));
     pl.kernel.fn<<<grid, pl.threads, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     d.stats.kernel_launches++;
     d.stats.grid = grid;
-    d.stats.stage_rows = p.stage_rows;
     if (which == 0 || d.cfg.precision == 32) {
         int resident = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, (const void *)pl.kernel.fn, pl.threads, smem) == cudaSuccess)

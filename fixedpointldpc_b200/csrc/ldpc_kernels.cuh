@@ -50,12 +50,7 @@ struct KParams {
     int max_iter;  // MAX_ITER; 0 = hard decision + syndrome only (iters output: 0 pass, 1 fail)
     uint32_t inv_m;  // floor(2^32 / m) + 1: i / m == umulhi(i, inv_m) for i < 2^16
     int precheck;  // decode_fixpoint's hardDecision pre-check
-    int claim_ahead;  // the CTA keeps `fifo_depth` frame indices claimed ahead of need (long queues only)
-    int fifo_depth;   // 1..MAX_FIFO
-    int stage_rows;   // rows of shared memory that receive the channel values of the first claimed frames by
-                      // cp.async.bulk (TMA 1-D) while the CTA decodes; 0: the refill reads global memory itself
-    int stage_stride; // bytes per row buffer (16-byte multiple, >= one frame's values + 32)
-    int tables_bytes; // degree tables kept in shared memory between the control block and the stage rows
+    int claim_ahead;  // every slot takes its next frame index one frame early (long queues only)
     // fed launches (host pipeline): frames [0, *avail) have arrived in `llr`; NULL: all of them
     const unsigned long long *avail;
     // fed launches: done_count[f / done_chunk] counts finished frames; the thread that completes a chunk sets the
@@ -389,8 +384,6 @@ __device__ __forceinline__ uint32_t cw_bit(const KParams &p, long long f, int v)
 constexpr int MAX_W = 16;         // word sets per CTA
 constexpr bool PREFETCH_VEDGE = true;   // software-prefetch the next variable's edge addresses (costs registers)
 constexpr int MAX_SLOTS = 2 * MAX_W;
-constexpr int MAX_FIFO = 8;       // frame indices a CTA keeps claimed ahead of need
-constexpr int MAX_STAGE = 4;      // stage rows (channel values of claimed frames, filled by cp.async.bulk)
 
 struct Ctrl {
     // Votes of one trip, read by that trip's stop decision.  Every thread takes the decision for itself, without a
@@ -399,75 +392,12 @@ struct Ctrl {
     uint32_t fail[3][MAX_W];   // per word set: lanes with at least one unsatisfied check (check phase)
     uint32_t gflag[3][MAX_W];  // per word set: lanes that left the guard range (variable phase / load; Packed16)
     int fid[MAX_SLOTS];     // frame index decoded in the slot, -1 = idle
-    int newfid[MAX_SLOTS];  // frame that moved into the slot in this trip (valid from the refill pass to the header update)
+    int next[MAX_SLOTS];    // frame the slot decodes after this one (taken from the queue one frame early), -1 = none
+    int newfid[MAX_SLOTS];  // frame moving into the slot during a refill
     unsigned int start[MAX_SLOTS];  // trip in which the slot's frame moved in: iterations completed = trip - start
     uint32_t lehmer[MAX_SLOTS];  // Lehmer state before the slot's frame (MC mode 2)
     unsigned int errs[MAX_SLOTS];  // info-bit errors of the frames being finished (MC mode)
-    // Frames the CTA has claimed from the queue ahead of need: the entry with sequence number e lives in
-    // q_fid[e % fifo_depth]; entries q_head .. q_head + fifo_depth - 1 exist, and those below q_staged have their
-    // channel values in stage row e % stage_rows (copy in flight or landed; mbarrier bar[row], phase parity q_par).
-    // Written by thread 0 in the header update (between the two barriers of a trip), read by everybody after the
-    // second one -- so all threads see the same queue when they plan a refill.
-    int q_fid[MAX_FIFO];
-    unsigned char q_par[MAX_FIFO];      // staged entries: phase parity of their row's mbarrier for this use
-    unsigned char q_row[MAX_FIFO];      // staged entries: their stage row
-    unsigned int q_head_idx;            // q_head % fifo_depth (kept so that nobody but thread 0 divides)
-    unsigned char row_uses[MAX_STAGE];  // bulk copies issued into each row so far (mod 256)
-    unsigned int q_head, q_staged;
-    long long avail;                    // frames [0, avail) have arrived (fed launches; otherwise all)
-    unsigned long long bar[MAX_STAGE];  // mbarriers of the stage rows
-    // State of the current trip (kept here rather than in registers: the two phases need every register they can get).
-    // Written before a barrier -- by thread 0, or by every thread with the same value -- and read behind it.
-    uint32_t active;    // slots that hold a frame
-    uint32_t served;    // slots the refill pass of this trip served (0: the trip had none)
-    uint32_t report;    // ... whose frame left in this trip
-    uint32_t taken;     // ... that received a frame
-    int ntake;          // entries taken from the queue of claimed frames
-    int drained;        // per-slot claims: the global queue is exhausted
-    unsigned long long claim;  // first of the `ntake` queue positions claimed to replace them
-    unsigned int dbg_frames;   // frames this CTA took (phase-timing builds print it)
 };
-
-// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-
-// shared-memory layout: [W][E] message words | [W][n] channel words | control block (16-byte aligned) | degree tables of
-// irregular codes | stage rows (16-byte aligned; the host passes the tables' size)
-// (offsets are added to the shared-memory base as plain pointer arithmetic -- the base itself is 16-byte aligned --
-// so that the compiler keeps the shared address space of everything derived from them: a round trip through an
-// integer turns every access to the control block into a generic one, and its shared atomics into global-style ATOMs)
-__device__ __forceinline__ Ctrl *ctrl_of(uint32_t *smem, int W, int E, int n)
-{
-    const unsigned int words = ((unsigned int)W * (unsigned int)(E + n) + 3u) & ~3u;
-    return reinterpret_cast<Ctrl *>(smem + words);
-}
-__device__ __forceinline__ char *stage_of(uint32_t *smem, int W, int E, int n, const KParams &p)
-{
-    const unsigned int words = ((unsigned int)W * (unsigned int)(E + n) + 3u) & ~3u;
-    const unsigned int bytes = (words * 4u + (unsigned int)sizeof(Ctrl) + (unsigned int)p.tables_bytes + 15u) & ~15u;
-    return reinterpret_cast<char *>(smem) + bytes;
-}
 
 // ------------------------------------------------------------------------------------------
 // check phase (ArrayLDPC_Decoder.cpp:66-118 + the syndrome of :296-333): NI independent check nodes of exact
@@ -570,7 +500,7 @@ __device__ __forceinline__ uint32_t check_node_any(uint32_t *e, int m, int d)
 
 // thread per (word-set group, check); the syndrome bits are OR-ed into fail[word set], one shared atomic per warp
 // CMASK: check degrees that get an exact body (bit d); a named irregular code lists its own, which keeps the hot
-// code small (the 802.11 code has degrees 7 and 8 only -- fifteen exact bodies would be 5 000 instructions)
+// code small (the 802.11 code has degrees 7 and 8 only -- fifteen exact bodies are 5 000 instructions)
 template <class T, int DC, bool REG, int NI, unsigned CMASK>
 __device__ __forceinline__ void check_phase(const KParams &p, uint32_t *fail, uint32_t *edge, const uint8_t *cdeg_s,
                                             int items, int m, int E, int W)
@@ -897,18 +827,6 @@ __device__ __noinline__ void variable_phase_parity(const KParams &p, Ctrl *ctrl,
 
 // ------------------------------------------------------------------------------------------
 // results of stopping frames, refill
-//
-// A trip of the main loop that has slots to serve (`want`: frames that stopped at the last decision, or idle slots
-// while the queue still has frames) runs
-//     refill pass     every thread plans the refill from the control block (same answer in every thread, no barrier):
-//                     results of the frames that leave, channel values of the frames that move in; ONE barrier
-//     variable phase  (the messages of a lane that received a frame were cleared by the refill pass, so this phase is
-//                     the reference's initialisation for it)
-//     [barrier]
-//     header update   slot owners / thread 0, while the other warps start the check phase: slot headers, Monte-Carlo
-//                     counters, the queue of claimed frames, bulk copies of the next frames into the stage rows
-// so a refill costs one extra barrier, and the latencies of the queue atomic and of the channel values (TMA bulk copy
-// into shared memory, issued a whole trip before the values are needed) stay off the critical path.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2(const void *ptr)
 {
@@ -921,6 +839,7 @@ __device__ __forceinline__ int queue_frame(const KParams &p, unsigned long long 
     return q < (unsigned long long)frames ? (p.index ? p.index[q] : (int)q) : -1;
 }
 
+// fed launches: frames [0, result) have arrived in global memory (the host's copy-in stream moves the mark)
 __device__ __forceinline__ long long frames_arrived(const KParams &p, long long frames)
 {
     if (!p.avail) return frames;
@@ -946,9 +865,8 @@ __device__ __forceinline__ void emit_word(const KParams &p, Ctrl *ctrl, int s, i
 // One slot of a decode-from-memory launch: the decoded bits of the frame that leaves (the hard decisions its last
 // variable phase left in the channel words, 32 consecutive variables per ballot) and the channel values of the
 // frame that moves in -- same thread, same word, so no barrier in between; four loads in flight per thread.
-// `bits_out` / `src`: rows of the two frames (NULL: nothing to write / no frame moves in, the words are left alone).
-// `src` points to global memory or to a stage row in shared memory.  Pointers advance by the CTA size instead of
-// being rebuilt per element.  Returns true if a value of this thread left the packed range.
+// `bits_out` / `src`: rows of the two frames (NULL: nothing to write / no frame).  Pointers advance by the CTA
+// size instead of being rebuilt per element.  Returns true if a value of this thread left the packed range.
 template <class T, class SRC>
 __device__ __forceinline__ bool swap_frame(uint32_t *lw, int lane, uint32_t *bits_out, const SRC *src, int n)
 {
@@ -972,7 +890,7 @@ __device__ __forceinline__ bool swap_frame(uint32_t *lw, int lane, uint32_t *bit
                     const uint32_t bits = __ballot_sync(0xffffffffu, mine && T::hd_bit(word[u * nthreads], lane));
                     if (leader && mine) bout[u * (nthreads >> 5)] = bits;
                 }
-                if (mine && in) {
+                if (mine) {
                     bool bad;
                     T::store_lane(&word[u * nthreads], lane, T::llr_lane(val[u], bad));
                     any_bad |= bad;
@@ -986,161 +904,82 @@ __device__ __forceinline__ bool swap_frame(uint32_t *lw, int lane, uint32_t *bit
     return any_bad;
 }
 
-// Where the next wanting slot gets its frame from.  Called by every thread for the slots of `want` in ascending
-// order with the same running state, so all threads plan the same refill without exchanging anything:
-//   sync  the slot's owner claimed a frame for it just now (ctrl->newfid, after a barrier)
-//   else  the oldest entry of the CTA's queue of claimed frames, if it exists, is a frame, and its values are there
-//         (in a stage row, or -- fed launches -- already arrived in global memory); entries are taken in order, so
-//         the first one that cannot be taken ends the refill and the remaining slots stay idle until the next trip
-struct Source {
-    int fn;   // frame that moves in, -1: none
-    int row;  // stage row holding its channel values, -1: read them from global memory
-    uint32_t parity;
-};
-struct Planner {
-    unsigned int head, head_idx, staged;
-    long long avail;
-    int taken;
-    bool blocked;
-};
-__device__ __forceinline__ Planner planner_init(const Ctrl *ctrl)
-{
-    return Planner{ctrl->q_head, ctrl->q_head_idx, ctrl->q_staged, ctrl->avail, 0, false};
-}
-__device__ __forceinline__ Source planner_next(const KParams &p, const Ctrl *ctrl, Planner &pl, int s, bool sync)
-{
-    if (sync) return Source{ctrl->newfid[s], -1, 0u};
-    if (pl.blocked || pl.taken >= p.fifo_depth) { pl.blocked = true; return Source{-1, -1, 0u}; }
-    const unsigned int e = pl.head + (unsigned int)pl.taken;
-    unsigned int idx = pl.head_idx + (unsigned int)pl.taken;  // e % fifo_depth
-    if (idx >= (unsigned int)p.fifo_depth) idx -= (unsigned int)p.fifo_depth;
-    const int f = ctrl->q_fid[idx];
-    if (f < 0) { pl.blocked = true; return Source{-1, -1, 0u}; }
-    if (e < pl.staged) {
-        ++pl.taken;
-        return Source{f, (int)ctrl->q_row[idx], (uint32_t)ctrl->q_par[idx]};
-    }
-    if (p.mc_mode == 0 && (long long)f >= pl.avail) { pl.blocked = true; return Source{-1, -1, 0u}; }
-    ++pl.taken;
-    return Source{f, -1, 0u};
-}
-
-// The refill pass of a trip.  `want`: slots to serve (frames that stopped at the last decision, idle slots asking for a
-// frame); `sync`: per-slot claims (first fill, short queues) instead of the CTA's queue of claimed frames.  Leaves
-// what it did in ctrl->served / report / taken / ntake / claim / active / drained for the header update and the stop
-// decision (ctrl->active itself is rewritten by the header update: every thread reads it here), and ends with the
-// barrier behind which the variable phase may run.  Returns the slots that hold a frame after the pass.
+// Results of the slots in `fin` (unless `first`), then the next frames move in: the lane's messages are cleared
+// and its channel values loaded or generated.  Zero messages make the next variable phase produce
+// post = LLR, v2c = LLR -- the reference's initialisation (ArrayLDPC_Decoder.cpp:45-61) -- for the new lane while
+// it runs an ordinary iteration for the lane's neighbour.  Returns the number of active slots.  Called by every
+// thread of the CTA (contains barriers).
 template <class T>
-__device__ __forceinline__ uint32_t refill_pass(const KParams &p, uint32_t *smem, uint32_t want, bool sync, int n, int E, int W,
-                                             unsigned int trip, int buf)
+__device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
+                                                 uint32_t fin, bool first, int n, int E, int W, long long frames,
+                                                 unsigned int trip, int buf)
 {
-    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
     const int nslots = W * T::LANES;
-    uint32_t *edge = smem, *llr = smem + (size_t)W * E;
-    Ctrl *ctrl = ctrl_of(smem, W, E, n);
-    const long long frames = p.count ? (long long)*p.count : p.frames;
-    const uint32_t before = ctrl->active;
-    const uint32_t report = want & before;  // slots whose frame leaves
-    const bool mine = tid < nslots && ((want >> tid) & 1u);  // one thread per slot (all in warp 0)
-    if (mine && ((report >> tid) & 1u)) {
+    const bool mine = tid < nslots && ((fin >> tid) & 1u);  // one thread per stopping slot (all in warp 0)
+    const bool emit = !first && (p.bits || p.mc_mode != 0);
+    unsigned long long claim = 0;
+    bool was_over = false;
+    int old_it = 0;
+    if (mine) {
         const int s = tid, w = s / T::LANES, lane = s % T::LANES;
-        const bool was_over = (ctrl->gflag[buf][w] >> lane) & 1u;
-        const int old_it = (int)(trip - 1u - ctrl->start[s]);  // decided at the end of trip - 1
-        p.iters[ctrl->fid[s]] = was_over ? -1 : (p.max_iter == 0 ? (int)((ctrl->fail[buf][w] >> lane) & 1u) : old_it);
+        was_over = (ctrl->gflag[buf][w] >> lane) & 1u;
+        old_it = (int)(trip - ctrl->start[s]);
+        if (!first)
+            p.iters[ctrl->fid[s]] = was_over ? -1 : (p.max_iter == 0 ? (int)((ctrl->fail[buf][w] >> lane) & 1u) : old_it);
+        // With claim_ahead the slot's next frame was taken from the queue (and its channel values pulled into L2)
+        // when the previous one moved in; the atomic issued here is for the frame after, and its round trip
+        // overlaps the passes below.
+        claim = atomicAdd(p.queue, 1ull);
+        const int f = p.claim_ahead ? ctrl->next[s] : queue_frame(p, claim, frames);
+        if (p.avail && f >= 0)  // fed launch: the frame's channel values may still be on their way (start of the batch only)
+            while (frames_arrived(p, frames) <= (long long)f) __nanosleep(200);
+        ctrl->newfid[s] = f;
+        if (p.mc_mode == 2 && f >= 0)
+            ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed, lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)f));
+        ctrl->errs[s] = 0u;
     }
-    if (sync) {
-        // first fill of the CTA, and every refill of a launch whose queue is too short to claim ahead
-        if (mine) {
-            const int s = tid;
-            const int f = queue_frame(p, atomicAdd(p.queue, 1ull), frames);
-            if (f >= 0 && p.avail)
-                while (frames_arrived(p, frames) <= (long long)f) __nanosleep(200);
-            ctrl->newfid[s] = f;
-        }
-        __syncthreads();
-    }
-    // ---- plan (identical in every thread)
-    uint32_t taken = 0;
-    int ntake = 0;
-    bool drained = false;
-    {
-        Planner pl = planner_init(ctrl);
-        for (uint32_t left = want; left; left &= left - 1u) {
-            const int s = __ffs(left) - 1;
-            const Source src = planner_next(p, ctrl, pl, s, sync);
-            if (src.fn >= 0) taken |= 1u << s;
-            else if (sync) drained = true;
-            if (mine && s == tid) {
-                if (!sync) ctrl->newfid[s] = src.fn;
-                if (p.mc_mode == 2 && src.fn >= 0)
-                    ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed, lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)src.fn));
-            }
-        }
-        ntake = pl.taken;
-    }
-    if (tid == 0) {
-        // the positions that replace the entries taken: the atomic's round trip overlaps this pass and the variable phase
-        unsigned long long claim = 0;
-        if (!sync && ntake > 0) claim = atomicAdd(p.queue, (unsigned long long)ntake);
-        ctrl->served = want; ctrl->report = report; ctrl->taken = taken; ctrl->ntake = ntake; ctrl->claim = claim;
-        ctrl->drained |= drained ? 1 : 0;
-    }
-
-    const bool emit = p.bits || p.mc_mode != 0;
-    if (p.mc_mode != 0) {
+    __syncthreads();
+    if (p.mc_mode != 0 && emit) {
         // Monte-Carlo mode generates the channel values with another thread-to-variable mapping, so the decoded
         // bits (kept in the channel words) are collected first
-        if (emit && report) {
-            for (uint32_t left = report; left; left &= left - 1u) {
-                const int s = __ffs(left) - 1;
-                const int fo = ctrl->fid[s];
-                const uint32_t *lw = llr + (size_t)(s / T::LANES) * n;
+        for (uint32_t left = fin; left; left &= left - 1u) {
+            const int s = __ffs(left) - 1;
+            const int fo = ctrl->fid[s];
+            const uint32_t *lw = llr + (size_t)(s / T::LANES) * n;
+            if (fo >= 0)
                 for (int base = 0; base < n; base += nthreads) {
                     const int v = base + tid;
                     emit_word(p, ctrl, s, fo, v, n, v < n ? T::hd_bit(lw[v], s % T::LANES) : 0u);
                 }
-            }
         }
-        __syncthreads();  // (also orders the owners' lehmer[] stores before their use below)
+        __syncthreads();
     }
     uint32_t bad_slots = 0;
-    Planner pl = planner_init(ctrl);
-    for (uint32_t left = want; left; left &= left - 1u) {
+    for (uint32_t left = fin; left; left &= left - 1u) {
         const int s = __ffs(left) - 1;
         const int w = s / T::LANES, lane = s % T::LANES;
-        const Source src = planner_next(p, ctrl, pl, s, sync);
-        const int fn = src.fn;
+        const int fo = emit ? ctrl->fid[s] : -1, fn = ctrl->newfid[s];
         uint32_t *ew = edge + (size_t)w * E, *lw = llr + (size_t)w * n;
         if (p.mc_mode == 0) {
-            const int fo = (emit && ((report >> s) & 1u)) ? ctrl->fid[s] : -1;
-            uint32_t *bits_out = fo >= 0 ? p.bits + (size_t)fo * p.nw32 : nullptr;
-            if (fn < 0 && !bits_out) continue;
+            uint32_t *bits_out = (fo >= 0 && p.bits) ? p.bits + (size_t)fo * p.nw32 : nullptr;
             bool bad;
-            if (fn >= 0 && src.row >= 0) {
-                // channel values staged in shared memory by cp.async.bulk; the copy started at the 16-byte line
-                // below the frame's first byte
-                mbar_wait(&ctrl->bar[src.row], src.parity);
-                const uintptr_t first = reinterpret_cast<uintptr_t>(p.llr) + (size_t)fn * n * 2u;
-                const int16_t *row = reinterpret_cast<const int16_t *>(stage_of(smem, W, E, n, p) + (size_t)src.row * p.stage_stride + (first & 15u));
-                bad = swap_frame<T>(lw, lane, bits_out, row, n);
-            } else if (p.llr_bits == 16) {
+            if (p.llr_bits == 16)
                 bad = swap_frame<T>(lw, lane, bits_out, fn >= 0 ? reinterpret_cast<const int16_t *>(p.llr) + (size_t)fn * n : nullptr, n);
-            } else {
+            else
                 bad = swap_frame<T>(lw, lane, bits_out, fn >= 0 ? reinterpret_cast<const int *>(p.llr) + (size_t)fn * n : nullptr, n);
-            }
             if (bad) bad_slots |= 1u << s;
-        } else if (fn < 0) {
-            continue;
         } else if (p.mc_mode == 1) {
             for (int q = tid; 4 * q < n; q += nthreads) {
-                float z[4];
-                philox_normals(p, p.mc_first + (unsigned long long)fn, (uint32_t)q, z);
+                float z[4] = {0.f, 0.f, 0.f, 0.f};
+                if (fn >= 0) philox_normals(p, p.mc_first + (unsigned long long)fn, (uint32_t)q, z);
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
                     const int v = 4 * q + h;
                     if (v < n) {
                         bool bad;
-                        T::store_lane(&lw[v], lane, T::llr_lane(quantise_llr(p, (double)z[h], cw_bit(p, fn, v)), bad));
+                        const int val = fn >= 0 ? quantise_llr(p, (double)z[h], cw_bit(p, fn, v)) : 0;
+                        T::store_lane(&lw[v], lane, T::llr_lane(val, bad));
                         if (bad) bad_slots |= 1u << s;
                     }
                 }
@@ -1148,130 +987,66 @@ __device__ __forceinline__ uint32_t refill_pass(const KParams &p, uint32_t *smem
         } else {
             for (int v = tid; v < n; v += nthreads) {
                 bool bad;
-                const int val = quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], p.mc_pow[v])), cw_bit(p, fn, v));
+                const int val = fn >= 0 ? quantise_llr(p, lehmer_normal(lehmer_mul(ctrl->lehmer[s], p.mc_pow[v])), cw_bit(p, fn, v)) : 0;
                 T::store_lane(&lw[v], lane, T::llr_lane(val, bad));
                 if (bad) bad_slots |= 1u << s;
             }
         }
-        // the messages of a lane that received a frame start from zero: the coming variable phase then computes
-        // post = LLR, v2c = LLR for it -- the reference's initialisation (ArrayLDPC_Decoder.cpp:45-61)
-        if (fn >= 0 && trip != 0u)
+        // its messages start from zero
+        if (!first)
             for (int i = tid; i < E; i += nthreads) T::store_lane(&ew[i], lane, 0u);
-    }
-    if (p.mc_mode != 0 && p.mc_pin_count > 0 && taken) {  // shortening: known positions pinned (PerfTest.cpp:410-414)
-        __syncthreads();
-        for (int i = tid; i < p.mc_pin_count; i += nthreads) {
-            const int v = p.mc_pin[i];
-            for (uint32_t left = taken; left; left &= left - 1u) {
-                const int s = __ffs(left) - 1;
-                bool bad;
-                T::store_lane(&llr[(size_t)(s / T::LANES) * n + v], s % T::LANES, T::llr_lane(p.mc_pin_value, bad));
-                if (bad) bad_slots |= 1u << s;
-            }
-        }
     }
     for (int s = 0; bad_slots; ++s, bad_slots >>= 1)  // judged by the coming trip's stop decision
         if (bad_slots & 1u) atomicOr(&ctrl->gflag[buf == 2 ? 0 : buf + 1][s / T::LANES], 1u << (s % T::LANES));
+    if (p.mc_mode != 0 && p.mc_pin_count > 0) {  // shortening: known positions pinned (PerfTest.cpp:410-414)
+        __syncthreads();
+        for (int i = tid; i < p.mc_pin_count; i += nthreads) {
+            const int v = p.mc_pin[i];
+            for (uint32_t left = fin; left; left &= left - 1u) {
+                const int s = __ffs(left) - 1;
+                if (ctrl->newfid[s] < 0) continue;
+                bool bad;
+                T::store_lane(&llr[(size_t)(s / T::LANES) * n + v], s % T::LANES, T::llr_lane(p.mc_pin_value, bad));
+                if (bad) atomicOr(&ctrl->gflag[buf == 2 ? 0 : buf + 1][s / T::LANES], 1u << (s % T::LANES));
+            }
+        }
+    }
     __syncthreads();
-    return (before & ~want) | taken;
-}
-
-// After a refill pass, between the barrier that ends the variable phase and the check phase (parity-mode launches:
-// before the variable phase, behind a barrier of its own): nothing here is read by the check phase, and everything
-// is read by all threads only after the barrier that ends it.
-//   slot owners  Monte-Carlo counters and completion signalling of the frames that left, new slot headers
-//   thread 0     the CTA's queue of claimed frames: entries that replace the ones taken, bulk copies of the channel
-//                values of the first `stage_rows` entries into their stage rows, the fed launch's arrival mark
-//   warp 0       L2 prefetch of the channel values the refill will read from global memory
-template <class T>
-__device__ __forceinline__ void header_update(const KParams &p, uint32_t *smem, bool sync, int n, int E, int W, unsigned int trip, int rbuf)
-{
-    const int tid = threadIdx.x, lane_id = tid & 31;
-    const int nslots = W * T::LANES;
-    Ctrl *ctrl = ctrl_of(smem, W, E, n);
-    const long long frames = p.count ? (long long)*p.count : p.frames;
-    const uint32_t want = ctrl->served, report = ctrl->report, taken = ctrl->taken;
-    const int ntake = ctrl->ntake;
-    if (tid == 0) ctrl->active = (ctrl->active & ~want) | taken;  // (the refill pass read the old value before its barrier)
-    if (tid < nslots && ((want >> tid) & 1u)) {
+    int ahead = -1;
+    if (mine) {
         const int s = tid;
-        if ((report >> s) & 1u) {
-            const int w = s / T::LANES, lane = s % T::LANES;
-            const bool was_over = (ctrl->gflag[rbuf][w] >> lane) & 1u;
-            const int fo = ctrl->fid[s];
-            if (p.mc_mode != 0 && !was_over) {  // flagged frames are counted by their exact re-decode
-                const unsigned int e = ctrl->errs[s];
-                if (p.mc_frame_err) p.mc_frame_err[fo] = (unsigned short)min(e, 65535u);
-                atomicAdd(&p.mc_counters[0], 1ull);
-                if (e) atomicAdd(&p.mc_counters[1], 1ull);
-                if (e) atomicAdd(&p.mc_counters[2], (unsigned long long)e);
-                atomicAdd(&p.mc_counters[3], (unsigned long long)(trip - 1u - ctrl->start[s]));
-            }
-            if (p.done_count) {
-                // results of frame fo (iteration count by this thread, bits by the ballot leaders before the barriers
-                // behind us) are complete: count it, and tell the host when its chunk is
-                const int chunk = fo / p.done_chunk;
-                const long long lo = (long long)chunk * p.done_chunk;
-                const unsigned int size = (unsigned int)min((long long)p.done_chunk, frames - lo);
-                __threadfence();
-                if (atomicAdd(&p.done_count[chunk], 1u) + 1u == size) {
-                    __threadfence_system();
-                    p.done_flag[chunk] = 1u;
-                }
+        if (!first && p.mc_mode != 0 && !was_over) {  // flagged frames are counted by their exact re-decode
+            const unsigned int e = ctrl->errs[s];
+            if (p.mc_frame_err) p.mc_frame_err[ctrl->fid[s]] = (unsigned short)min(e, 65535u);
+            atomicAdd(&p.mc_counters[0], 1ull);
+            if (e) atomicAdd(&p.mc_counters[1], 1ull);
+            if (e) atomicAdd(&p.mc_counters[2], (unsigned long long)e);
+            atomicAdd(&p.mc_counters[3], (unsigned long long)old_it);
+        }
+        if (!first && p.done_count && ctrl->fid[s] >= 0) {
+            // results of the frame that left (iteration count by this thread, bits by the ballot leaders before the
+            // barrier behind us) are complete: count it, and tell the host when its chunk is
+            const int fo = ctrl->fid[s], chunk = fo / p.done_chunk;
+            const long long lo = (long long)chunk * p.done_chunk;
+            const unsigned int size = (unsigned int)min((long long)p.done_chunk, frames - lo);
+            __threadfence();
+            if (atomicAdd(&p.done_count[chunk], 1u) + 1u == size) {
+                __threadfence_system();
+                p.done_flag[chunk] = 1u;
             }
         }
-        ctrl->errs[s] = 0u;
-#ifdef LDPC_PHASE_TIMING
-        if ((taken >> s) & 1u) atomicAdd(&ctrl->dbg_frames, 1u);
-#endif
-        ctrl->fid[s] = ((taken >> s) & 1u) ? ctrl->newfid[s] : -1;
-        ctrl->start[s] = trip;  // its first (initialising) variable phase runs in this trip
+        ctrl->fid[s] = ctrl->newfid[s];
+        ctrl->start[s] = trip + 1u;  // its first (initialising) variable phase runs in the coming trip
+        if (p.claim_ahead) {
+            ahead = queue_frame(p, claim, frames);
+            ctrl->next[s] = ahead;
+        }
     }
-    if (sync && !p.claim_ahead) return;
-    if (tid == 0) {
-        const unsigned int L = (unsigned int)p.fifo_depth, S = (unsigned int)p.stage_rows;
-        unsigned int head = ctrl->q_head;
-        if (sync) {
-            // first trip of a launch that claims ahead: fill the queue (the slots took their frames before it)
-            const unsigned long long base = atomicAdd(p.queue, (unsigned long long)L);
-            for (unsigned int k = 0; k < L; ++k) ctrl->q_fid[k] = queue_frame(p, base + k, frames);
-        } else {
-            const unsigned long long claim = ctrl->claim;
-            for (int k = 0; k < ntake; ++k)
-                ctrl->q_fid[(head + L + (unsigned int)k) % L] = queue_frame(p, claim + (unsigned long long)k, frames);
-            head += (unsigned int)ntake;
-            ctrl->q_head = head;
-            ctrl->q_head_idx = head % L;
-        }
-        const long long avail = frames_arrived(p, frames);
-        ctrl->avail = avail;
-        unsigned int staged = max(ctrl->q_staged, head);
-        if (S > 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the rows were read through the generic proxy
-            char *stage = stage_of(smem, W, E, n, p);
-            const size_t bytes = (size_t)n * 2u;
-            for (; staged < head + S; ++staged) {
-                const int f = ctrl->q_fid[staged % L];
-                if (f < 0 || (long long)f >= avail) break;
-                const uintptr_t first = reinterpret_cast<uintptr_t>(p.llr) + (size_t)f * bytes;
-                const uintptr_t lo = first & ~(uintptr_t)15u;
-                const uint32_t len = (uint32_t)(((first + bytes + 15u) & ~(uintptr_t)15u) - lo);
-                unsigned long long *bar = &ctrl->bar[staged % S];
-                ctrl->q_row[staged % L] = (unsigned char)(staged % S);
-                ctrl->q_par[staged % L] = ctrl->row_uses[staged % S] & 1u;  // a row is skipped when its entry is read directly
-                ctrl->row_uses[staged % S]++;
-                mbar_expect_tx(bar, len);
-                bulk_copy_g2s(stage + (size_t)(staged % S) * p.stage_stride, reinterpret_cast<const void *>(lo), len, bar);
-            }
-        }
-        ctrl->q_staged = staged;
-    }
-    if (!sync && p.mc_mode == 0 && tid < 32 && ntake > 0 && p.stage_rows < p.fifo_depth && !p.avail) {
-        // entries that will not be staged: pull their channel values into L2, they are read a frame time from now
-        const unsigned long long claim = ctrl->claim;
+    if (p.claim_ahead && p.mc_mode == 0 && tid < 32 && !p.avail) {
+        // pull the channel values of the frames just claimed into L2: they are read one frame time from now
         const size_t bytes = (size_t)n * (p.llr_bits >> 3);
-        for (int k = 0; k < ntake; ++k) {
-            const int f = queue_frame(p, claim + (unsigned long long)k, frames);
+        for (uint32_t left = fin; left; left &= left - 1u) {
+            const int f = __shfl_sync(0xffffffffu, ahead, __ffs(left) - 1);
             if (f >= 0) {
                 const char *first_byte = reinterpret_cast<const char *>(p.llr) + (size_t)f * bytes;
                 const char *line = first_byte - (reinterpret_cast<uintptr_t>(first_byte) & 127u) + (size_t)lane_id * 128u;
@@ -1279,6 +1054,10 @@ __device__ __forceinline__ void header_update(const KParams &p, uint32_t *smem, 
             }
         }
     }
+    __syncthreads();
+    int active = 0;
+    for (int s = 0; s < nslots; ++s) active += ctrl->fid[s] >= 0;
+    return active;
 }
 
 // Stop / continue decision of every slot, taken after the check phase (its votes are the syndrome of the state the
@@ -1286,26 +1065,18 @@ __device__ __forceinline__ void header_update(const KParams &p, uint32_t *smem, 
 // MAX_ITER (:63), decode_fixpoint's pre-check on the channel hard decisions (:443-450, iteration count 0), the
 // hard-decision-only mode (max_iter == 0) and lanes that left the packed range.  Every warp evaluates all slots
 // (lane = slot) from words nobody writes before the next barrier, so the mask of stopping slots is the same in
-// every thread and no barrier is needed to agree on it.  Idle slots ask for a frame while the CTA's queue of
-// claimed frames has one.
+// every thread and no barrier is needed to agree on it.
 template <class T>
-__device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, int W, bool fifo, unsigned int trip, int buf)
+__device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, int W, unsigned int trip, int buf)
 {
     const int s = threadIdx.x & 31;
-    const uint32_t active = ctrl->active;
     bool stop = false;
-    if (s < W * T::LANES) {
-        if ((active >> s) & 1u) {
-            const int w = s / T::LANES, lane = s % T::LANES;
-            const int it = (int)(trip - ctrl->start[s]);  // 0: the frame has only been initialised
-            const bool pass = !((ctrl->fail[buf][w] >> lane) & 1u);
-            const bool over = (ctrl->gflag[buf][w] >> lane) & 1u;
-            stop = it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over;
-        } else if (fifo) {
-            stop = ctrl->q_fid[ctrl->q_head_idx] >= 0;
-        } else {
-            stop = !ctrl->drained;  // short queue: idle slots claim for themselves while frames are left
-        }
+    if (s < W * T::LANES && ctrl->fid[s] >= 0) {
+        const int w = s / T::LANES, lane = s % T::LANES;
+        const int it = (int)(trip - ctrl->start[s]);  // 0: the frame has only been initialised
+        const bool pass = !((ctrl->fail[buf][w] >> lane) & 1u);
+        const bool over = (ctrl->gflag[buf][w] >> lane) & 1u;
+        stop = it >= p.max_iter || (pass && (it >= 1 || p.precheck)) || over;
     }
     const uint32_t fin = __ballot_sync(0xffffffffu, stop);
     // the buffer the trip after next votes into (last read one decision ago, before two barriers)
@@ -1314,7 +1085,6 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
         ctrl->fail[clr][threadIdx.x] = 0u;
         ctrl->gflag[clr][threadIdx.x] = 0u;
     }
-    if (threadIdx.x == 0 && fin == 0u) ctrl->served = 0u;  // no refill pass in the coming trip
     return fin;
 }
 
@@ -1350,94 +1120,63 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
     const int n = N ? N : p.n, m = M ? M : p.m, E = EA ? EA : (M ? DC * M : p.E), W = p.W;
     uint32_t *edge = smem;                 // [W][E]
     uint32_t *llr = edge + (size_t)W * E;  // [W][n] channel values (+ the hard decision of the last posterior)
-    Ctrl *ctrl = ctrl_of(smem, W, E, n);
-    // degree tables next to the control block (irregular codes dispatch on them once per node and phase); the stage
-    // rows follow them (stage_of)
+    Ctrl *ctrl = reinterpret_cast<Ctrl *>(llr + (size_t)W * n);
+    // degree tables next to the control block (irregular codes dispatch on them once per node and phase)
     constexpr bool REGV = PREFETCH_VEDGE && M != 0 && REG && DV <= 8 && ARRP == 0;
     uint8_t *cdeg_s = reinterpret_cast<uint8_t *>(ctrl + 1);
     uint8_t *vdeg_s = cdeg_s + (REG ? 0 : ((m + 15) & ~15));
     if (!REG) for (int i = tid; i < m; i += nthreads) cdeg_s[i] = p.cdeg[i];
     if (!REGV && !ARRP) for (int i = tid; i < n; i += nthreads) vdeg_s[i] = p.vdeg[i];
     const int nslots = W * T::LANES;
+    const long long frames = p.count ? (long long)*p.count : p.frames;
 
     for (int i = tid; i < W * (E + n); i += nthreads) smem[i] = 0u;
     if (tid < MAX_W)
         for (int b = 0; b < 3; ++b) { ctrl->fail[b][tid] = 0u; ctrl->gflag[b][tid] = 0u; }
     if (tid < MAX_SLOTS) {
-        ctrl->fid[tid] = -1; ctrl->start[tid] = 0u; ctrl->newfid[tid] = -1; ctrl->errs[tid] = 0u; ctrl->lehmer[tid] = 0u;
-    }
-    if (tid < MAX_FIFO) { ctrl->q_fid[tid] = -1; ctrl->q_par[tid] = 0; ctrl->q_row[tid] = 0; }
-    if (tid == 0) {
-        ctrl->q_head = 0u; ctrl->q_head_idx = 0u; ctrl->q_staged = 0u; ctrl->avail = 0;
-        ctrl->dbg_frames = 0u;
-        ctrl->active = 0u; ctrl->served = 0u; ctrl->report = 0u; ctrl->taken = 0u; ctrl->ntake = 0; ctrl->drained = 0; ctrl->claim = 0ull;
-        for (int r = 0; r < MAX_STAGE; ++r) { mbar_init(&ctrl->bar[r], 1u); ctrl->row_uses[r] = 0; }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ctrl->fid[tid] = -1; ctrl->start[tid] = 0u; ctrl->newfid[tid] = -1;
+        ctrl->next[tid] = (p.claim_ahead && tid < nslots) ? queue_frame(p, atomicAdd(p.queue, 1ull), frames) : -1;
     }
     __syncthreads();
 
     const int items = (W / NI) * m;  // (word-set group, check)
 #ifdef LDPC_PHASE_TIMING
     long long t_phase[4] = {0, 0, 0, 0}, t_mark = clock64();
-    long long t_start;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 #define LDPC_MARK(k) do { long long t_now = clock64(); t_phase[k] += t_now - t_mark; t_mark = t_now; } while (0)
 #else
 #define LDPC_MARK(k) do { } while (0)
 #endif
 
-    // slots to serve at the top of the trip: stopped frames, idle slots asking for a frame
-    uint32_t want = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);
-    // trip t votes into buffer t % 3; `buf` is the buffer of the trip that ended last (what a refill reports from).
-    // The first fill (trip 0) claims per slot; later refills take the frames the CTA claimed ahead.
+    uint32_t fin = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);  // slots to (re)fill
+    bool first = true;
+    // trip t votes into buffer t % 3; `buf` is the buffer of the trip that ended last (what a refill reports from)
     unsigned int trip = 0;
     int buf = 2;
     for (;;) {
-        const bool sync = trip == 0u || !p.claim_ahead;
-        uint32_t holding = 1u;
-        if (want) holding = refill_pass<T>(p, smem, want, sync, n, E, W, trip, buf);
-        if (!holding) {
-            // nothing to decode right now: finish the bookkeeping, then either leave or (fed launch whose next
-            // frames have not arrived yet) look again
-            if (want || p.claim_ahead) header_update<T>(p, smem, sync, n, E, W, trip, buf);
-            __syncthreads();
-            const bool more = p.claim_ahead ? ctrl->q_fid[ctrl->q_head_idx] >= 0 : !ctrl->drained;
-            if (!more) break;
-            __syncthreads();  // q_* were read above; thread 0 rewrites them in the next header update
-            __nanosleep(500);
-            want = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);
-            ++trip;
-            continue;
+        if (fin) {
+            // trip - 1 is the trip whose stop decision released the slots
+            const int active = finish_and_refill<T>(p, ctrl, edge, llr, fin, first, n, E, W, frames, trip - 1u, buf);
+            if (active == 0) break;
+            first = false;
         }
-        const int rbuf = buf;
         buf = buf == 2 ? 0 : buf + 1;
         LDPC_MARK(0);
-        if (p.post || p.v2c) {
-            if (want) {  // the parity-mode variable phase looks up the frame of every lane (`want`, not ctrl->served:
-                         // thread 0 rewrote that word after the last barrier)
-                header_update<T>(p, smem, sync, n, E, W, trip, rbuf);
-                __syncthreads();
-            }
-            variable_phase_parity<T, DV, REGV, ARRP, VMASK>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s);
-        } else if (ARRP) {
-            variable_phase_array<T, DV, (ARRP ? ARRP : 1), false>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E);
-        } else {
-            variable_phase<T, DV, false, REGV, VMASK>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s);
-        }
+        if (p.post || p.v2c) variable_phase_parity<T, DV, REGV, ARRP, VMASK>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s);
+        else if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), false>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E);
+        else variable_phase<T, DV, false, REGV, VMASK>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s);
         __syncthreads();
         LDPC_MARK(1);
-        if (ctrl->served && !(p.post || p.v2c)) header_update<T>(p, smem, sync, n, E, W, trip, rbuf);
         check_phase<T, DC, REG, NI, CMASK>(p, ctrl->fail[buf], edge, cdeg_s, items, m, E, W);
         __syncthreads();
         LDPC_MARK(2);
-        want = stop_decision<T>(p, ctrl, W, p.claim_ahead != 0, trip, buf);
+        fin = stop_decision<T>(p, ctrl, W, trip, buf);
         ++trip;
         LDPC_MARK(3);
     }
 #ifdef LDPC_PHASE_TIMING
-    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 1 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1) && trip > 0)
-        printf("phase cycles (CTA %d): results+refill %lld variable %lld check %lld stop decision %lld | trips %u frames %u t0 %lld\n",
-               (int)blockIdx.x, t_phase[0], t_phase[1], t_phase[2], t_phase[3], trip, ctrl->dbg_frames, t_start);
+    if (tid == 0 && blockIdx.x == 0 && trip > 0)
+        printf("phase cycles (CTA 0): results+refill %lld variable %lld check %lld stop decision %lld | trips %u\n", t_phase[0],
+               t_phase[1], t_phase[2], t_phase[3], trip);
 #endif
 }
 

@@ -159,9 +159,8 @@ typedef struct {
     int grid;                  /* CTAs per launch                                             */
     int smem_bytes;            /* dynamic shared memory per CTA (packed kernel)               */
     int smem_bytes32;
-    int stage_rows;            /* rows of shared memory the last launch filled by TMA bulk copies (0: none) */
     int resident_ctas_per_sm;  /* cudaOccupancyMaxActiveBlocksPerMultiprocessor of the last decode launch     */
-    int launch_smem_bytes;     /* dynamic shared memory of the last decode launch (word sets + stage rows)    */
+    int launch_smem_bytes;     /* dynamic shared memory of the last decode launch                             */
 } ldpc_decoder_stats;
 
 int ldpc_decoder_get_stats(const ldpc_decoder *dec, ldpc_decoder_stats *out);
