@@ -2,8 +2,8 @@
 Eb/N0 points (array p47 r24: 10 000), CUDA engine through the C ABI with parity-mode outputs against the CPU oracle on
 all host cores; iteration counts, decoded bits, posteriors and final messages compared frame by frame through CRC-32
 digests.  About 100 s on the B200 box (16 host cores); LDPC_SCALE_FRAMES shrinks it."""
-import importlib.util
 import os
+import sys
 
 import pytest
 
@@ -14,9 +14,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.timeout(900)
 def test_full_state_parity_at_scale(capsys):
-    spec = importlib.util.spec_from_file_location("parity_at_scale", os.path.join(ROOT, "scripts", "parity_at_scale.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))  # (a plain import: the worker processes of its pool import it too)
+    import parity_at_scale as mod
     frames = os.environ.get("LDPC_SCALE_FRAMES", "100000")
     rc = mod.main(["--frames", frames])
     out = capsys.readouterr().out
