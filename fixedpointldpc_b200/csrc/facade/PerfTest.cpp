@@ -87,6 +87,11 @@ Point simulate(FP_Decoder &Decoder, bool fixpoint, double snr, double sigma, con
     memset(&cfg, 0, sizeof cfg);
     cfg.snr = snr; cfg.sigma = sigma;
     cfg.stream = LDPC_STREAM_REFERENCE; cfg.seed = g_stream_state;
+    // LDPC_STREAM=philox: the counter-based stream (float Box-Muller, several times cheaper per frame than the
+    // reference's double-precision inverse normal) for long waterfall points; the counters then differ from the
+    // reference's by Monte-Carlo noise only
+    const char *stream_env = getenv("LDPC_STREAM");
+    if (stream_env && !strcmp(stream_env, "philox")) cfg.stream = LDPC_STREAM_PHILOX;
     cfg.codeword = codeword ? &(*codeword)[0] : NULL;
     cfg.info_index = info_index ? &(*info_index)[0] : NULL;
     cfg.info_count = info_index ? (int)info_index->size() : 0;
