@@ -113,6 +113,8 @@ Point simulate(FP_Decoder &Decoder, bool fixpoint, double snr, double sigma, con
         stop.iters_cap = log.size();
     }
     ldpc_mc_result res;
+    // NCCL writes its banner / debug lines to stdout unless told otherwise; stdout is the reference's transcript
+    if (R > 1) setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     int rc = ldpc_mc_run_multi(&dec[0], R, &cfg, &stop, &res);
     if (rc != LDPC_OK) ldpc_facade::fail("simulation", rc);
     Point pt;
