@@ -939,7 +939,12 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
             ctrl->lehmer[s] = lehmer_mul((uint32_t)p.mc_seed, lehmer_pow(p.mc_jump, p.mc_first + (unsigned long long)f));
         ctrl->errs[s] = 0u;
     }
-    __syncthreads();
+    // Decode-from-memory launches that claim ahead need no barrier here: the frame that moves in is ctrl->next[s],
+    // written one refill ago, and nothing the owner stores above is read by the other threads before the next barrier.
+    // (Monte-Carlo launches read lehmer[] / errs[], sync claims read newfid[], fed launches wait for the owner's
+    // arrival check.)
+    const bool quick = p.claim_ahead && p.mc_mode == 0 && !p.avail;
+    if (!quick) __syncthreads();
     if (p.mc_mode != 0 && emit) {
         // Monte-Carlo mode generates the channel values with another thread-to-variable mapping, so the decoded
         // bits (kept in the channel words) are collected first
@@ -959,7 +964,7 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
     for (uint32_t left = fin; left; left &= left - 1u) {
         const int s = __ffs(left) - 1;
         const int w = s / T::LANES, lane = s % T::LANES;
-        const int fo = emit ? ctrl->fid[s] : -1, fn = ctrl->newfid[s];
+        const int fo = emit ? ctrl->fid[s] : -1, fn = quick ? ctrl->next[s] : ctrl->newfid[s];
         uint32_t *ew = edge + (size_t)w * E, *lw = llr + (size_t)w * n;
         if (p.mc_mode == 0) {
             uint32_t *bits_out = (fo >= 0 && p.bits) ? p.bits + (size_t)fo * p.nw32 : nullptr;
