@@ -109,6 +109,22 @@ def test_no_cpu_fallback_without_device(fp):
     assert e.value.status == capi.ERR_NO_DEVICE
 
 
+def test_new_entry_points_reject_null_arguments_without_a_device():
+    """Argument checks of the round-2 entries run before any CUDA call (no compute on a CPU-only box)."""
+    import ctypes as C
+    from fixedpointldpc_b200 import capi
+    L = capi.load_library()
+    err = C.c_int(0)
+    assert not L.ldpc_mc_group_create(None, 0, C.byref(err)) and err.value == capi.ERR_ARG
+    assert L.ldpc_mc_group_size(None) == 0
+    assert L.ldpc_mc_group_run(None, None, None, None) == capi.ERR_ARG
+    assert L.ldpc_mc_run_multi(None, 0, None, None, None) == capi.ERR_ARG
+    assert L.ldpc_decode_batch_f64(None, None, 1, None, None, None, None) == capi.ERR_ARG
+    assert L.ldpc_decode_batch_i16(None, None, 1, None, None, None, None) == capi.ERR_ARG
+    assert L.ldpc_decoder_device(None) == capi.ERR_ARG and not L.ldpc_decoder_code(None)
+    L.ldpc_mc_group_destroy(None)
+
+
 def test_product_does_not_reference_the_oracle():
     pkg = os.path.join(ROOT, "fixedpointldpc_b200")
     for dirpath, _, files in os.walk(pkg):
