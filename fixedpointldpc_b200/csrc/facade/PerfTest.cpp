@@ -291,7 +291,7 @@ int EncodeTrial(char *info, int MaxPacket)
 
 // The sweep the reference's signature promises (db_start, db_end, db_step) but never runs, with the CSV it
 // opens but never writes.  All-zero codeword, every position counted.
-int ArrayLDPC_Sweep(double db_start, double db_end, double db_step, const char *Filename, int frame_errors)
+int ArrayLDPC_Sweep(double db_start, double db_end, double db_step, const char *Filename, int frame_errors, int short_len)
 {
     class FP_Decoder Decoder;
 #if LDPC_CODE_VARIANT == 0
@@ -305,6 +305,24 @@ int ArrayLDPC_Sweep(double db_start, double db_end, double db_step, const char *
     const double rate = Decoder.getRate();
     const bool fixpoint = true;
 #endif
+    // Shortening (BASELINE config 3; the rule of ArrayLDPC_Debug_Shorten, PerfTest.cpp:355, 410-414, for any code): the
+    // information positions come from a generator derived from H (ldpc_gen_from_code: the reference ships no G for the
+    // cut code), the first short_len of them are known zeros pinned to LLR 7 * 2^FRAC_WIDTH, the channel rate counts
+    // the remaining ones, and calculateBER looks at the information positions only.
+    std::vector<int32_t> info, pins;
+    double sweep_rate = rate;
+    if (short_len > 0) {
+        int err = LDPC_OK, n = 0, rows = 0, k = 0;
+        ldpc_gen *gen = ldpc_gen_from_code(Decoder.code(), NULL, 0, &err);
+        if (!gen) ldpc_facade::fail("generator from H", err);
+        ldpc_gen_dims(gen, &n, &rows, &k);
+        info.resize(k);
+        ldpc_gen_indices(gen, &info[0], NULL);
+        ldpc_gen_free(gen);
+        if (short_len > k) short_len = k;
+        pins.assign(info.begin(), info.begin() + short_len);
+        sweep_rate = double(k - short_len) / n;
+    }
     ofstream csv(Filename, std::ios::app);
     if (!csv) { std::cerr << "failed to open " << Filename << endl; return 1; }
     csv << "EbN0_dB,frames,frame_errors,bit_errors,FER,BER,avg_iters" << endl;
@@ -312,8 +330,9 @@ int ArrayLDPC_Sweep(double db_start, double db_end, double db_step, const char *
     // histogram of the decoder's return values (frames per iteration count 0..MAX_ITER), GPUs used and wall time
     ofstream log((std::string(Filename) + "_log.txt").c_str(), std::ios::app);
     for (double db = db_start; db <= db_end + 1e-9; db += (db_step > 0 ? db_step : 1.0)) {
-        double snr = 2 * pow(10.0, db / 10) * rate, sigma = sqrt(1 / snr);
-        Point p = simulate(Decoder, fixpoint, snr, sigma, NULL, NULL, NULL, 0, COUNT_INFO_BIT_ERRORS, frame_errors, 0, NULL);
+        double snr = 2 * pow(10.0, db / 10) * sweep_rate, sigma = sqrt(1 / snr);
+        Point p = simulate(Decoder, fixpoint, snr, sigma, NULL, short_len > 0 ? &info : NULL, short_len > 0 ? &pins : NULL,
+                           7 * (1 << FRAC_WIDTH), COUNT_INFO_BIT_ERRORS, frame_errors, 0, NULL);
         csv << db << "," << p.Counter << "," << p.pckerror << "," << p.biterror << "," << p.pckerror / p.Counter << ","
             << p.biterror / p.Counter / CWD_LENGTH << "," << double(p.iter_sum) / p.Counter << endl;
         if (log) {

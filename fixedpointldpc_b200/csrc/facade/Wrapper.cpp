@@ -4,7 +4,7 @@
 //   wrapper <db_start> <db_end> <db_step> <csv>   ArrayLDPC_PerfTest           (argc == 5, Wrapper.cpp:23-28)
 //   wrapper                                       ArrayLDPC_Debug_Wifi, Eb/N0 read from stdin (Wrapper.cpp:29-33)
 //   wrapper debug | shorten <len> | decodetrial <dB> <frames> | encodetrial <frames> | timetrial <dB> <frames>
-//   wrapper sweep <db_start> <db_end> <db_step> <csv> [frame_errors]
+//   wrapper sweep <db_start> <db_end> <db_step> <csv> [frame_errors] [short_len]
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -30,7 +30,8 @@ int main(int argc, char *argv[])
             return EncodeTrial(info, atoi(argv[2]));
         }
         if (argc >= 6 && !strcmp(argv[1], "sweep"))
-            return ArrayLDPC_Sweep(atof(argv[2]), atof(argv[3]), atof(argv[4]), argv[5], argc >= 7 ? atoi(argv[6]) : 100);
+            return ArrayLDPC_Sweep(atof(argv[2]), atof(argv[3]), atof(argv[4]), argv[5], argc >= 7 ? atoi(argv[6]) : 100,
+                                   argc >= 8 ? atoi(argv[7]) : 0);
         if (argc == 5) {
             // the reference parses nothing and always runs (2, 2, 1, "test.csv"); the arguments are honoured here
             return ArrayLDPC_PerfTest(atof(argv[1]), atof(argv[2]), atof(argv[3]), argv[4]);

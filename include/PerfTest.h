@@ -15,8 +15,11 @@ int EncodeTrial(char *info, int MaxPacket);
 int ArrayLDPC_Debug_Shorten(int short_len);
 
 /* Extensions the reference stubs out: a real Eb/N0 sweep with CSV rows
- * "EbN0_dB,frames,frame_errors,bit_errors,FER,BER,avg_iters" appended to Filename. */
-int ArrayLDPC_Sweep(double db_start, double db_end, double db_step, const char *Filename, int frame_errors);
+ * "EbN0_dB,frames,frame_errors,bit_errors,FER,BER,avg_iters" appended to Filename and one line per point in
+ * Filename_log.txt (histogram of the decoder's return values, GPUs, wall time).  short_len > 0: the first short_len
+ * information positions (generator derived from H) are known zeros pinned to LLR 7*2^FRAC_WIDTH, like
+ * ArrayLDPC_Debug_Shorten does for the array code (BASELINE config 3 on the cut79 variant). */
+int ArrayLDPC_Sweep(double db_start, double db_end, double db_step, const char *Filename, int frame_errors, int short_len = 0);
 /* State of the process-wide noise stream (rngs.cpp:45-49 keeps it in a file-static; default 123456789). */
 void LDPC_PutSeed(long x);
 long LDPC_GetSeed();

@@ -63,3 +63,43 @@ def test_cut79_shortened_sweep_counters_equal_oracle(fp, po, tmp_path):
     grp.close()
     for d in decs:
         d.close()
+
+
+def test_console_sweep_on_shortened_cut79_equals_oracle(fp, po, tmp_path):
+    """`ldpc_wrapper_c79 sweep 3.8 4.6 0.4 out.csv 10 300`: the console program's shortened sweep (all-zero codeword,
+    generator derived from H, first 300 information positions pinned, reference noise stream continuing from point to
+    point like the reference's file-static RNG state) against the same loop run sequentially on the CPU oracle."""
+    import subprocess
+    from conftest import ROOT
+    code = fp.codes.cut79()
+    t = tables_of(code)
+    gen = fp.Generator(code=code)
+    short_len, target = 300, 10
+    pins = gen.info_index[:short_len].astype(np.int32)
+    rate = (gen.k - short_len) / code.n
+    exe = os.path.join(ROOT, "fixedpointldpc_b200", "ldpc_wrapper_c79")
+    res = subprocess.run([exe, "sweep", "3.8", "4.6", "0.4", "out.csv", str(target), str(short_len)], capture_output=True,
+                         text=True, cwd=str(tmp_path), timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    rows = open(os.path.join(tmp_path, "out.csv")).read().strip().split("\n")[1:]
+    orc = po.Oracle(t)
+    orc.seed.value = 123456789                      # rngs.cpp:45; never re-seeded between points
+    zeros = np.zeros(gen.k, np.int32)
+    db, want = 3.8, []
+    while db <= 4.6 + 1e-9:
+        snr = 2 * 10.0 ** (db / 10) * rate
+        sigma = np.sqrt(1 / snr)
+        frames = bit_errors = frame_errors = iter_sum = 0
+        while frame_errors < target:
+            llr = orc.channel_frame(None, code.n, snr, sigma)
+            llr[pins] = 7 * 16
+            it, bits, _, _ = orc.decode(llr)
+            e = orc.calculate_ber(bits, gen.info_index, zeros)
+            frames += 1; bit_errors += e; frame_errors += e > 0; iter_sum += it
+        want.append((frames, frame_errors, bit_errors, iter_sum))
+        db += 0.4
+    assert len(rows) == len(want) == 3
+    for row, (frames, fe, be, its) in zip(rows, want):
+        cols = row.split(",")
+        assert (int(cols[1]), int(cols[2]), int(cols[3])) == (frames, fe, be), (row, frames, fe, be)
+        assert abs(float(cols[6]) - its / frames) < 1e-4 * max(1.0, its / frames)
