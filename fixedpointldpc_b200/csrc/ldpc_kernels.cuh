@@ -182,6 +182,11 @@ struct Scalar32 {
     {
         return (uint32_t)abs(val) | ((uint32_t)val & SIGN) | (val <= 0 ? HD : 0u);
     }
+    // refill pass: the lane's hard-decision bit in a channel word, the stored form of a channel value, its range check
+    __device__ static __forceinline__ uint32_t hd_mask(int) { return HD; }
+    __device__ static __forceinline__ uint32_t llr_word(int val) { return (uint32_t)val; }
+    __device__ static __forceinline__ uint32_t range_key(int) { return 0u; }
+    __device__ static __forceinline__ bool range_bad(uint32_t) { return false; }
     __device__ static __forceinline__ void store_lane(uint32_t *word, int, uint32_t x) { *word = x; }
 };
 
@@ -277,6 +282,11 @@ struct Packed16 {
         bad = (uint32_t)(val + LLR_LIMIT - 1) >= 2u * LLR_LIMIT - 1u;  // |val| >= LLR_LIMIT
         return (uint32_t)val & 0xffffu;
     }
+    // |val| >= LLR_LIMIT  <=>  (uint32_t)(val + LLR_LIMIT - 1) >= 2 * LLR_LIMIT - 1: the refill keeps the maximum of the keys
+    __device__ static __forceinline__ uint32_t hd_mask(int lane) { return lane ? 0x40000000u : 0x00004000u; }
+    __device__ static __forceinline__ uint32_t llr_word(int val) { return (uint32_t)val & 0xffffu; }
+    __device__ static __forceinline__ uint32_t range_key(int val) { return (uint32_t)(val + LLR_LIMIT - 1); }
+    __device__ static __forceinline__ bool range_bad(uint32_t key) { return key >= 2u * LLR_LIMIT - 1u; }
     __device__ static __forceinline__ uint32_t init_lane(int val)
     {
         // a value outside the guard range was flagged when it was loaded; only its low 14 magnitude bits are kept here
@@ -867,41 +877,56 @@ __device__ __forceinline__ void emit_word(const KParams &p, Ctrl *ctrl, int s, i
 // frame that moves in -- same thread, same word, so no barrier in between; four loads in flight per thread.
 // `bits_out` / `src`: rows of the two frames (NULL: nothing to write / no frame).  Pointers advance by the CTA
 // size instead of being rebuilt per element.  Returns true if a value of this thread left the packed range.
-template <class T, class SRC>
-__device__ __forceinline__ bool swap_frame(uint32_t *lw, int lane, uint32_t *bits_out, const SRC *src, int n)
+// BITS / LOAD select the two halves at compile time, the hard-decision bit of the lane is one mask for the whole pass,
+// and the range check of the packed kernel is a running maximum tested once (T::range_key / T::range_bad) -- the pass
+// is paid in issue slots (profiles/r02/launch_shape_sweep.txt).
+template <class T, class SRC, bool BITS, bool LOAD>
+__device__ __forceinline__ bool swap_frame_pass(uint32_t *lw, int lane, uint32_t *bits_out, const SRC *src, int n)
 {
     constexpr int UNR = 4;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const bool leader = (tid & 31) == 0;
+    const uint32_t hd = T::hd_mask(lane);
     uint32_t *word = lw + tid;
-    uint32_t *bout = bits_out ? bits_out + (tid >> 5) : nullptr;
-    const SRC *in = src ? src + tid : nullptr;
-    bool any_bad = false;
+    uint32_t *bout = bits_out + (tid >> 5);
+    const SRC *in = src + tid;
+    uint32_t key = 0u;
     for (int v0 = tid; v0 - tid < n; v0 += UNR * nthreads) {
         int val[UNR];
+        if (LOAD) {
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) val[u] = (in && v0 + u * nthreads < n) ? (int)in[u * nthreads] : 0;
+            for (int u = 0; u < UNR; ++u) val[u] = v0 + u * nthreads < n ? (int)in[u * nthreads] : 0;
+        }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int v = v0 + u * nthreads;
             if (v - tid < n) {  // the same for every thread of the CTA
                 const bool mine = v < n;
-                if (bout) {
-                    const uint32_t bits = __ballot_sync(0xffffffffu, mine && T::hd_bit(word[u * nthreads], lane));
+                if (BITS) {
+                    const uint32_t w = mine ? word[u * nthreads] : 0u;
+                    const uint32_t bits = __ballot_sync(0xffffffffu, (w & hd) != 0u);
                     if (leader && mine) bout[u * (nthreads >> 5)] = bits;
                 }
-                if (mine) {
-                    bool bad;
-                    T::store_lane(&word[u * nthreads], lane, T::llr_lane(val[u], bad));
-                    any_bad |= bad;
+                if (LOAD && mine) {
+                    T::store_lane(&word[u * nthreads], lane, T::llr_word(val[u]));
+                    key = max(key, T::range_key(val[u]));
                 }
             }
         }
         word += UNR * nthreads;
-        if (bout) bout += UNR * (nthreads >> 5);
-        if (in) in += UNR * nthreads;
+        if (BITS) bout += UNR * (nthreads >> 5);
+        if (LOAD) in += UNR * nthreads;
     }
-    return any_bad;
+    return T::range_bad(key);
+}
+
+template <class T, class SRC>
+__device__ __forceinline__ bool swap_frame(uint32_t *lw, int lane, uint32_t *bits_out, const SRC *src, int n)
+{
+    if (bits_out && src) return swap_frame_pass<T, SRC, true, true>(lw, lane, bits_out, src, n);
+    if (src) return swap_frame_pass<T, SRC, false, true>(lw, lane, bits_out, src, n);
+    if (bits_out) return swap_frame_pass<T, SRC, true, false>(lw, lane, bits_out, src, n);
+    return false;
 }
 
 // Results of the slots in `fin` (unless `first`), then the next frames move in: the lane's messages are cleared
@@ -998,8 +1023,10 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
             }
         }
         // its messages start from zero
-        if (!first)
+        if (!first) {
+#pragma unroll 4
             for (int i = tid; i < E; i += nthreads) T::store_lane(&ew[i], lane, 0u);
+        }
     }
     for (int s = 0; bad_slots; ++s, bad_slots >>= 1)  // judged by the coming trip's stop decision
         if (bad_slots & 1u) atomicOr(&ctrl->gflag[buf == 2 ? 0 : buf + 1][s / T::LANES], 1u << (s % T::LANES));
