@@ -897,7 +897,9 @@ static int decode_host(ldpc_decoder *d, const void *llr_v, int llr_bits, size_t 
         const ldpc::Plan &pl = d->cfg.precision == 32 ? d->plan32 : d->plan16;
         const size_t per_grid = (size_t)d->sm_count * pl.kernel.ctas_per_sm * pl.W * (d->cfg.precision == 32 ? 1 : 2);
         if (!post && !v2c && d->cfg.max_iter > 0 && frames >= 8 * per_grid && !getenv("LDPC_NO_FEED")) {
-            const size_t batch = (size_t)1 << 18;
+            size_t batch = (size_t)1 << 18;
+            if (const char *env = getenv("LDPC_FEED_BATCH"))  // (tests exercise the batch loop with small batches)
+                if (atol(env) > 0) batch = std::max<size_t>((size_t)atol(env), 8 * per_grid);
             for (size_t base = 0; base < frames; base += batch) {
                 const size_t cnt = std::min(batch, frames - base);
                 int rc = decode_host_fed(d, llr + base * c.n * esz, llr_bits, cnt, iters + base, bits ? bits + base * nw32 : nullptr);

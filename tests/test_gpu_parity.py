@@ -335,12 +335,18 @@ def test_fed_host_pipeline_equals_chunked_pipeline(fp, po, name, bits16):
     run = (lambda: dec.decode_i16(llr.astype(np.int16))) if bits16 else (lambda: dec.decode(llr))
     os.environ.pop("LDPC_NO_FEED", None)
     a = run()
+    os.environ["LDPC_FEED_BATCH"] = "15000"      # several fed launches per call (the default batch is 2^18 frames)
+    try:
+        c = run()
+    finally:
+        os.environ.pop("LDPC_FEED_BATCH", None)
     os.environ["LDPC_NO_FEED"] = "1"
     try:
         b = run()
     finally:
         os.environ.pop("LDPC_NO_FEED", None)
     assert (a["iters"] == b["iters"]).all() and (a["bits"] == b["bits"]).all()
+    assert (c["iters"] == b["iters"]).all() and (c["bits"] == b["bits"]).all()
     assert dec.stats()["fallback_frames"] >= 3
     orc = po.Oracle(t)
     for f in (0, 5, 1234, 20000, frames - 1):
