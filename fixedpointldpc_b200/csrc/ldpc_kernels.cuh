@@ -1129,6 +1129,8 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
 //        that is less than DC*M (irregular named code)
 //   ARRP forward square array code with this circulant size: edge addresses in closed form (variable_phase_array)
 //   VMASK, CMASK  irregular codes: the variable / check degrees that get exact bodies (all ones: every degree up to DV / DC)
+//   WS   word sets per CTA as a compile-time constant (0: p.W): the named codes run with the W their plan computes, and
+//        the loops over word sets / word-set groups then have one shape instead of three
 //   MAXT, NCTA  launch bounds: CTA size and co-resident CTAs per SM.  Co-resident CTAs drift out of phase, so
 //        one's latency-bound variable phase overlaps the other's ALU-bound check phase.
 //
@@ -1142,14 +1144,14 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
 // so a frame that stops costs one check phase more than the reference executes, and a converged frame is
 // found by the same two barriers per trip that the phases need anyway.
 // ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA, int ARRP, unsigned VMASK, unsigned CMASK>
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA, int ARRP, unsigned VMASK, unsigned CMASK, int WS>
 __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constant__ KParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x, nthreads = blockDim.x;
     // the named codes get their dimensions as compile-time constants: every k*m word offset of the check
     // phase then folds into the load/store immediate
-    const int n = N ? N : p.n, m = M ? M : p.m, E = EA ? EA : (M ? DC * M : p.E), W = p.W;
+    const int n = N ? N : p.n, m = M ? M : p.m, E = EA ? EA : (M ? DC * M : p.E), W = WS ? WS : p.W;
     uint32_t *edge = smem;                 // [W][E]
     uint32_t *llr = edge + (size_t)W * E;  // [W][n] channel values (+ the hard decision of the last posterior)
     Ctrl *ctrl = reinterpret_cast<Ctrl *>(llr + (size_t)W * n);
