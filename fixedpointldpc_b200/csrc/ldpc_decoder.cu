@@ -29,8 +29,8 @@ typedef void (*kernel_fn)(const KParams);
 
 struct KernelChoice {
     kernel_fn fn = nullptr;
-    kernel_fn fn_ws = nullptr;  // the same kernel with the word-set count `ws` compiled in (named codes)
-    int ws = 0;
+    kernel_fn fn_ws = nullptr;  // the same kernel with the word-set count `ws` and the CTA size `ts` compiled in (named codes)
+    int ws = 0, ts = 0;
     int max_threads = 0;
     int ni = 1;
     int ctas_per_sm = 1;
@@ -38,17 +38,18 @@ struct KernelChoice {
 };
 
 template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA = 0, int ARRP = 0, unsigned VMASK = 0xffffffffu,
-          unsigned CMASK = 0xffffffffu, int WS16 = 0, int WS32 = 0>
+          unsigned CMASK = 0xffffffffu, int WS16 = 0, int WS32 = 0, int TS = 0>
 static KernelChoice make_choice()
 {
     KernelChoice k;
-    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA, ARRP, VMASK, CMASK, 0>;
+    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA, ARRP, VMASK, CMASK, 0, 0>;
     // word sets per CTA the plan arrives at without overrides (packed and int32 kernels have the same count: a word set
     // is E + n words either way)
     constexpr int WS = T::LANES == 2 ? WS16 : WS32;
     if (WS > 0) {
-        k.fn_ws = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA, ARRP, VMASK, CMASK, WS>;
+        k.fn_ws = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA, ARRP, VMASK, CMASK, WS, TS>;
         k.ws = WS;
+        k.ts = TS;
     }
     k.max_threads = MAXT;
     k.ni = NI;
@@ -95,7 +96,7 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
         // closed-form edge addresses measured +1 % at 30 iterations, +2 % at the operating point over the table with
         // its one-variable prefetch (profiles/r02/launch_shape_sweep.txt); LDPC_A5_TABLE=1 keeps the table
         if (!getenv("LDPC_A5_TABLE") && is_forward_array(c, 47))
-            return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209, 0, 47, 0xffffffffu, 0xffffffffu, 1, 1>();
+            return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209, 0, 47, 0xffffffffu, 0xffffffffu, 1, 1, 256>();
         return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209>();
     }
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 24 && c.m == 1128 && c.n == 2209 && is_forward_array(c, 47))  // array p47 r24
@@ -104,10 +105,10 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
         // picks 384 threads: 12 warps x 3 passes cover the 36 warp-loads of checks exactly, three warps per scheduler
         // (0.60 M frames/s against 0.53 M for 576 threads / 96 registers, 0.58 M for 640).  LDPC_A24_640=1: the 96-register build.
         if (getenv("LDPC_A24_640")) return make_choice<T, 47, true, 24, 1, 640, 1, 1128, 2209, 0, 47>();
-        return make_choice<T, 47, true, 24, 1, 512, 1, 1128, 2209, 0, 47, 0xffffffffu, 0xffffffffu, 1, 1>();
+        return make_choice<T, 47, true, 24, 1, 512, 1, 1128, 2209, 0, 47, 0xffffffffu, 0xffffffffu, 1, 1, 384>();
     }
     if (regular && vregular && c.dc_max == 28 && c.dv_max == 4 && c.m == 316 && c.n == 2212)          // cut79
-        return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212, 0, 0, 0xffffffffu, 0xffffffffu, 2, 2>();
+        return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212, 0, 0, 0xffffffffu, 0xffffffffu, 2, 2, 640>();
     int full = 0, last = 0;  // words per word set with the checks sorted by descending degree (see ldpc_decoder::e_words)
     for (int d : c.cdeg) { full += (d >= c.dc_max - 1); last += (d == c.dc_max); }
     if (c.dc_max == 8 && c.dv_max <= 12 && c.m == 972 && c.n == 1944 && full == 972 && last == 162) {  // 802.11n 1944 r1/2
@@ -115,7 +116,7 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
         bool only = true;
         for (int d : c.vdeg) only &= (d == 2 || d == 3 || d == 4 || d == 11);
         if (only && !getenv("LDPC_WIFI_ALL_DEGREES"))
-            return make_choice<T, 8, false, 12, 3, 512, 2, 972, 1944, 7 * 972 + 162, 0, (1u << 2) | (1u << 3) | (1u << 4) | (1u << 11), (1u << 7) | (1u << 8), 3, 3>();
+            return make_choice<T, 8, false, 12, 3, 512, 2, 972, 1944, 7 * 972 + 162, 0, (1u << 2) | (1u << 3) | (1u << 4) | (1u << 11), (1u << 7) | (1u << 8), 3, 3, 512>();
         return make_choice<T, 8, false, 12, 3, 512, 2, 972, 1944, 7 * 972 + 162>();  // three word sets per CTA and thread
     }
     // any other code: run-time dimensions
@@ -219,7 +220,7 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
         if (e >= best_e - 0.03) best_t = t;  // largest CTA within 3% of the best lane efficiency
     }
     if (want_threads > 0) best_t = std::min(k.max_threads, std::max(32, (want_threads / 32) * 32));
-    if (k.fn_ws && W == k.ws && !getenv("LDPC_RUNTIME_W")) k.fn = k.fn_ws;
+    if (k.fn_ws && W == k.ws && (k.ts == 0 || best_t == k.ts) && !getenv("LDPC_RUNTIME_W")) k.fn = k.fn_ws;
     out.kernel = k; out.W = W; out.threads = best_t;
     out.smem = W * per_w + (int)sizeof(Ctrl) + tables;
     // the attribute belongs to the kernel instantiation, not to this decoder: decoders that share an instantiation

@@ -513,9 +513,9 @@ __device__ __forceinline__ uint32_t check_node_any(uint32_t *e, int m, int d)
 // code small (the 802.11 code has degrees 7 and 8 only -- fifteen exact bodies are 5 000 instructions)
 template <class T, int DC, bool REG, int NI, unsigned CMASK>
 __device__ __forceinline__ void check_phase(const KParams &p, uint32_t *fail, uint32_t *edge, const uint8_t *cdeg_s,
-                                            int items, int m, int E, int W)
+                                            int items, int m, int E, int W, int nthreads)
 {
-    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
+    const int tid = threadIdx.x, lane_id = tid & 31;
     if (!REG) {
         // irregular code: the checks of a warp's pass have one degree (p.corder), one group of NI word sets at a time
         for (int wg = 0; wg < W / NI; ++wg) {
@@ -751,7 +751,7 @@ __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, 
 // VMASK: variable degrees that get an exact body (bit d), see CMASK
 template <class T, int DV, bool PARITY, bool REGV, unsigned VMASK>
 __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
-                                               int n, int E, const uint8_t *vdeg)
+                                               int n, int E, const uint8_t *vdeg, int nthreads)
 {
     if (REGV) {
         uint32_t gacc[2] = {0u, 0u};  // guard bits of the thread's variables in word sets 0 and 1
@@ -759,11 +759,11 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
         uint32_t next[DV];
 #pragma unroll
         for (int j = 0; j < DV; ++j) next[j] = v < n ? (uint32_t)p.vedge[j * n + v] * 4u : 0u;
-        for (; v < n; v += blockDim.x) {
+        for (; v < n; v += nthreads) {
             uint32_t off[DV];
 #pragma unroll
             for (int j = 0; j < DV; ++j) off[j] = next[j];
-            const int vn = v + blockDim.x;
+            const int vn = v + nthreads;
 #pragma unroll
             for (int j = 0; j < DV; ++j) next[j] = vn < n ? (uint32_t)p.vedge[j * n + vn] * 4u : 0u;
             variable_node_acc<T, DV, PARITY>(p, ctrl, gflag, gacc, edge, llr, v, W, n, E, off);
@@ -774,7 +774,7 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
         uint32_t vnext = p.vorder[threadIdx.x];
         for (int k = 0; k < p.vorder_k; ++k) {
             const int v = (int)vnext;
-            if (k + 1 < p.vorder_k) vnext = p.vorder[(k + 1) * blockDim.x + threadIdx.x];
+            if (k + 1 < p.vorder_k) vnext = p.vorder[(k + 1) * nthreads + threadIdx.x];
             if (v == 0xffff) continue;
             const int dv = vdeg[v];
             bool done = false;
@@ -803,11 +803,11 @@ __device__ __forceinline__ void variable_phase(const KParams &p, Ctrl *ctrl, uin
 // L2 in a phase that is latency-bound (the host verifies the code against this formula before choosing the kernel).
 template <class T, int DV, int P, bool PARITY>
 __device__ __forceinline__ void variable_phase_array(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr,
-                                                     int W, int n, int m, int E)
+                                                     int W, int n, int m, int E, int nthreads)
 {
     uint32_t gacc[2] = {0u, 0u};
     constexpr uint32_t INV_P = (uint32_t)((1ull << 32) / P) + 1u;  // v / P == umulhi(v, INV_P) for v < 2^16
-    for (int v = threadIdx.x; v < n; v += blockDim.x) {
+    for (int v = threadIdx.x; v < n; v += nthreads) {
         const uint32_t b = __umulhi((uint32_t)v, INV_P);
         uint32_t u = ((uint32_t)v - b * P) * 4u;       // 4 * t_a
         const uint32_t row = b * (uint32_t)m * 4u;      // byte offset of slot b
@@ -829,10 +829,10 @@ __device__ __forceinline__ void variable_phase_array(const KParams &p, Ctrl *ctr
 // register needs do not shape the allocation of the throughput path
 template <class T, int DV, bool REGV, int ARRP, unsigned VMASK>
 __device__ __noinline__ void variable_phase_parity(const KParams &p, Ctrl *ctrl, uint32_t *gflag, uint32_t *edge, uint32_t *llr, int W,
-                                                   int n, int m, int E, const uint8_t *vdeg)
+                                                   int n, int m, int E, const uint8_t *vdeg, int nthreads)
 {
-    if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), true>(p, ctrl, gflag, edge, llr, W, n, m, E);
-    else variable_phase<T, DV, true, REGV, VMASK>(p, ctrl, gflag, edge, llr, W, n, E, vdeg);
+    if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), true>(p, ctrl, gflag, edge, llr, W, n, m, E, nthreads);
+    else variable_phase<T, DV, true, REGV, VMASK>(p, ctrl, gflag, edge, llr, W, n, E, vdeg, nthreads);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -881,10 +881,10 @@ __device__ __forceinline__ void emit_word(const KParams &p, Ctrl *ctrl, int s, i
 // and the range check of the packed kernel is a running maximum tested once (T::range_key / T::range_bad) -- the pass
 // is paid in issue slots (profiles/r02/launch_shape_sweep.txt).
 template <class T, class SRC, bool BITS, bool LOAD>
-__device__ __forceinline__ bool swap_frame_pass(uint32_t *lw, int lane, uint32_t *bits_out, const SRC *src, int n)
+__device__ __forceinline__ bool swap_frame_pass(uint32_t *lw, int lane, uint32_t *bits_out, const SRC *src, int n, int nthreads)
 {
     constexpr int UNR = 4;
-    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int tid = threadIdx.x;
     const bool leader = (tid & 31) == 0;
     const uint32_t hd = T::hd_mask(lane);
     uint32_t *word = lw + tid;
@@ -921,11 +921,11 @@ __device__ __forceinline__ bool swap_frame_pass(uint32_t *lw, int lane, uint32_t
 }
 
 template <class T, class SRC>
-__device__ __forceinline__ bool swap_frame(uint32_t *lw, int lane, uint32_t *bits_out, const SRC *src, int n)
+__device__ __forceinline__ bool swap_frame(uint32_t *lw, int lane, uint32_t *bits_out, const SRC *src, int n, int nthreads)
 {
-    if (bits_out && src) return swap_frame_pass<T, SRC, true, true>(lw, lane, bits_out, src, n);
-    if (src) return swap_frame_pass<T, SRC, false, true>(lw, lane, bits_out, src, n);
-    if (bits_out) return swap_frame_pass<T, SRC, true, false>(lw, lane, bits_out, src, n);
+    if (bits_out && src) return swap_frame_pass<T, SRC, true, true>(lw, lane, bits_out, src, n, nthreads);
+    if (src) return swap_frame_pass<T, SRC, false, true>(lw, lane, bits_out, src, n, nthreads);
+    if (bits_out) return swap_frame_pass<T, SRC, true, false>(lw, lane, bits_out, src, n, nthreads);
     return false;
 }
 
@@ -937,9 +937,9 @@ __device__ __forceinline__ bool swap_frame(uint32_t *lw, int lane, uint32_t *bit
 template <class T>
 __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, uint32_t *edge, uint32_t *llr,
                                                  uint32_t fin, bool first, int n, int E, int W, long long frames,
-                                                 unsigned int trip, int buf)
+                                                 unsigned int trip, int buf, int nthreads)
 {
-    const int tid = threadIdx.x, nthreads = blockDim.x, lane_id = tid & 31;
+    const int tid = threadIdx.x, lane_id = tid & 31;
     const int nslots = W * T::LANES;
     const bool mine = tid < nslots && ((fin >> tid) & 1u);  // one thread per stopping slot (all in warp 0)
     const bool emit = !first && (p.bits || p.mc_mode != 0);
@@ -995,9 +995,9 @@ __device__ __forceinline__ int finish_and_refill(const KParams &p, Ctrl *ctrl, u
             uint32_t *bits_out = (fo >= 0 && p.bits) ? p.bits + (size_t)fo * p.nw32 : nullptr;
             bool bad;
             if (p.llr_bits == 16)
-                bad = swap_frame<T>(lw, lane, bits_out, fn >= 0 ? reinterpret_cast<const int16_t *>(p.llr) + (size_t)fn * n : nullptr, n);
+                bad = swap_frame<T>(lw, lane, bits_out, fn >= 0 ? reinterpret_cast<const int16_t *>(p.llr) + (size_t)fn * n : nullptr, n, nthreads);
             else
-                bad = swap_frame<T>(lw, lane, bits_out, fn >= 0 ? reinterpret_cast<const int *>(p.llr) + (size_t)fn * n : nullptr, n);
+                bad = swap_frame<T>(lw, lane, bits_out, fn >= 0 ? reinterpret_cast<const int *>(p.llr) + (size_t)fn * n : nullptr, n, nthreads);
             if (bad) bad_slots |= 1u << s;
         } else if (p.mc_mode == 1) {
             for (int q = tid; 4 * q < n; q += nthreads) {
@@ -1129,8 +1129,9 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
 //        that is less than DC*M (irregular named code)
 //   ARRP forward square array code with this circulant size: edge addresses in closed form (variable_phase_array)
 //   VMASK, CMASK  irregular codes: the variable / check degrees that get exact bodies (all ones: every degree up to DV / DC)
-//   WS   word sets per CTA as a compile-time constant (0: p.W): the named codes run with the W their plan computes, and
-//        the loops over word sets / word-set groups then have one shape instead of three
+//   WS, TS  word sets per CTA and CTA size as compile-time constants (0: p.W / blockDim.x): the named codes run with the
+//        shape their plan computes; the loops over word sets and over the CTA's passes then have one shape and constant
+//        trip counts (measured +3 to +6 % on all four codes, profiles/r02/launch_shape_sweep.txt)
 //   MAXT, NCTA  launch bounds: CTA size and co-resident CTAs per SM.  Co-resident CTAs drift out of phase, so
 //        one's latency-bound variable phase overlaps the other's ALU-bound check phase.
 //
@@ -1144,11 +1145,11 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
 // so a frame that stops costs one check phase more than the reference executes, and a converged frame is
 // found by the same two barriers per trip that the phases need anyway.
 // ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA, int ARRP, unsigned VMASK, unsigned CMASK, int WS>
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA, int ARRP, unsigned VMASK, unsigned CMASK, int WS, int TS>
 __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constant__ KParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int tid = threadIdx.x, nthreads = TS ? TS : (int)blockDim.x;
     // the named codes get their dimensions as compile-time constants: every k*m word offset of the check
     // phase then folds into the load/store immediate
     const int n = N ? N : p.n, m = M ? M : p.m, E = EA ? EA : (M ? DC * M : p.E), W = WS ? WS : p.W;
@@ -1189,18 +1190,18 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
     for (;;) {
         if (fin) {
             // trip - 1 is the trip whose stop decision released the slots
-            const int active = finish_and_refill<T>(p, ctrl, edge, llr, fin, first, n, E, W, frames, trip - 1u, buf);
+            const int active = finish_and_refill<T>(p, ctrl, edge, llr, fin, first, n, E, W, frames, trip - 1u, buf, nthreads);
             if (active == 0) break;
             first = false;
         }
         buf = buf == 2 ? 0 : buf + 1;
         LDPC_MARK(0);
-        if (p.post || p.v2c) variable_phase_parity<T, DV, REGV, ARRP, VMASK>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s);
-        else if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), false>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E);
-        else variable_phase<T, DV, false, REGV, VMASK>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s);
+        if (p.post || p.v2c) variable_phase_parity<T, DV, REGV, ARRP, VMASK>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, vdeg_s, nthreads);
+        else if (ARRP) variable_phase_array<T, DV, (ARRP ? ARRP : 1), false>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, m, E, nthreads);
+        else variable_phase<T, DV, false, REGV, VMASK>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s, nthreads);
         __syncthreads();
         LDPC_MARK(1);
-        check_phase<T, DC, REG, NI, CMASK>(p, ctrl->fail[buf], edge, cdeg_s, items, m, E, W);
+        check_phase<T, DC, REG, NI, CMASK>(p, ctrl->fail[buf], edge, cdeg_s, items, m, E, W, nthreads);
         __syncthreads();
         LDPC_MARK(2);
         fin = stop_decision<T>(p, ctrl, W, trip, buf);
