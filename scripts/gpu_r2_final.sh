@@ -1,8 +1,8 @@
 #!/bin/bash
-# round 2, call O: final ncu captures of the shipped kernels (summaries only), then whole suite + smoke + both bench arms
+# round 2, call R: final ncu captures of the shipped kernels (summaries only), then whole suite + smoke + both bench arms
 set -x
 cd "$GRAFT_REPO_ROOT" || exit 1
-O=gpurun_out/r2o; mkdir -p $O
+O=gpurun_out/r2r; mkdir -p $O
 for c in wifi a5 c79 a24; do
   timeout 400 ncu --set full --import-source on --clock-control none -k regex:decode_kernel -s 3 -c 1 -o $O/prof_${c} -f \
     python bench.py --code $c --only --precision 16 --steps 1 --warmup 3 --no-cpu --frames 16384 > $O/ncu_${c}.log 2>&1
