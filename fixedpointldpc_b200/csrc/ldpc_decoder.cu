@@ -95,6 +95,10 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 5 && c.m == 235 && c.n == 2209) {        // array p47 r5
         // closed-form edge addresses measured +1 % at 30 iterations, +2 % at the operating point over the table with
         // its one-variable prefetch (profiles/r02/launch_shape_sweep.txt); LDPC_A5_TABLE=1 keeps the table
+        // experiment: two word sets per CTA, 480 threads (470 checks on 15 warps instead of 235 on 8: 2 % idle lanes in
+        // the check phase instead of 8 %), two CTAs per SM
+        if (getenv("LDPC_A5_W2") && is_forward_array(c, 47))
+            return make_choice<T, 47, true, 5, 1, 480, 2, 235, 2209, 0, 47, 0xffffffffu, 0xffffffffu, 2, 2, 480>();
         if (!getenv("LDPC_A5_TABLE") && is_forward_array(c, 47))
             return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209, 0, 47, 0xffffffffu, 0xffffffffu, 1, 1, 256>();
         return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209>();
