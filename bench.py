@@ -532,7 +532,7 @@ def main():
     ap.add_argument("--precision", type=int, default=0, choices=[0, 16, 32])
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--frames-per-cta", type=int, default=0)
-    ap.add_argument("--e2e-frames", type=int, default=1 << 16)
+    ap.add_argument("--e2e-frames", type=int, default=1 << 17, help="frames per end-to-end call (capped at the step's frames)")
     ap.add_argument("--cpu-frames-per-core", type=int, default=256, help="--impl reference: frames per core and step")
     ap.add_argument("--cpu-baseline-frames-per-core", type=int, default=0,
                     help="GPU arm: frames per core of the cpu_baseline leg (default: about 10 s of CPU work)")

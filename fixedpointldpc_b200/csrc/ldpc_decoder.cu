@@ -95,10 +95,7 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 5 && c.m == 235 && c.n == 2209) {        // array p47 r5
         // closed-form edge addresses measured +1 % at 30 iterations, +2 % at the operating point over the table with
         // its one-variable prefetch (profiles/r02/launch_shape_sweep.txt); LDPC_A5_TABLE=1 keeps the table
-        // experiment: two word sets per CTA, 480 threads (470 checks on 15 warps instead of 235 on 8: 2 % idle lanes in
-        // the check phase instead of 8 %), two CTAs per SM
-        if (getenv("LDPC_A5_W2") && is_forward_array(c, 47))
-            return make_choice<T, 47, true, 5, 1, 480, 2, 235, 2209, 0, 47, 0xffffffffu, 0xffffffffu, 2, 2, 480>();
+        // (two word sets per CTA on 480 threads, two CTAs per SM: same rate at 30 iterations, 3 % slower at 4.5 dB)
         if (!getenv("LDPC_A5_TABLE") && is_forward_array(c, 47))
             return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209, 0, 47, 0xffffffffu, 0xffffffffu, 1, 1, 256>();
         return make_choice<T, 47, true, 5, 1, 256, 4, 235, 2209>();
@@ -795,12 +792,15 @@ static int decode_host_fed(ldpc_decoder *d, const char *llr, int llr_bits, size_
     int rc = ldpc::ensure_staging(*d, frames, false, false);
     if (rc != LDPC_OK) return rc;
     const size_t nchunks = (frames + done_chunk - 1) / done_chunk;
-    // copy-in chunks: one frame per slot first (the decode starts after a short copy), then 4096 frames at a time.  The
+    // copy-in chunks of at most 4096 frames.  The
     // arrival mark trails the copy by up to a chunk, so chunks stay small: on a box whose copy-in rate is only a little
     // above the decode rate (eight GPUs copying at once: 23 GB/s per GPU against 55 GB/s alone) a kernel that has caught
     // up with the mark idles for the rest of the chunk in flight (doubling chunks up to 32 768 frames cost 15 % there).
     std::vector<size_t> marks;
-    for (size_t at = 0, sz = std::max<size_t>(slots, 1024); at < frames; sz = 4096) {
+    // The first chunks are short (256 frames, doubling up to 4096) so that the first CTAs start decoding some tens
+    // of microseconds after the launch instead of after one frame per slot has arrived.
+    const bool ramp = !getenv("LDPC_FEED_NO_RAMP");
+    for (size_t at = 0, sz = ramp ? 256 : std::max<size_t>(slots, 1024); at < frames; sz = ramp ? std::min<size_t>(4096, sz * 2) : 4096) {
         at = std::min(frames, at + sz);
         marks.push_back(at);
     }

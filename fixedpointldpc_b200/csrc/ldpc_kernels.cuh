@@ -149,8 +149,15 @@ struct Scalar32 {
     // posterior word + its hard decision in message position (bit = post <= 0, quirk Q3)
     template <int D> __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd)
     {
-        hd = ((uint32_t)(a.v - 1) >> 1) & HD;  // sign of post-1, moved to bit 30
+        hd = (uint32_t)(a.v - 1) >> 1;  // sign of post-1, moved to bit 30 (the users mask with HD)
         return (uint32_t)a.v;
+    }
+    template <int D> __device__ static __forceinline__ uint32_t posterior(uint32_t lx, const uint32_t *x, uint32_t &hd)
+    {
+        Acc acc = acc_init(lx);
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc_sub(acc, x[j]);
+        return post_word<D>(acc, hd);
     }
     // sign | magnitude of post + (-c2v); the caller ORs the hard-decision bit in
     __device__ static __forceinline__ uint32_t v2c_signmag(uint32_t post, uint32_t nc)
@@ -170,7 +177,7 @@ struct Scalar32 {
     // A channel word also carries the hard decision of the variable's last posterior in bit 30, which is a copy of
     // the sign bit as long as |LLR| < 2^30: llr_restore() gives the channel value back, llr_with_hd() stores the bit.
     __device__ static __forceinline__ uint32_t llr_restore(uint32_t x) { return (x & ~HD) | ((x >> 1) & HD); }
-    __device__ static __forceinline__ uint32_t llr_with_hd(uint32_t x, uint32_t hd) { return (x & ~HD) | hd; }
+    __device__ static __forceinline__ uint32_t llr_with_hd(uint32_t x, uint32_t hd) { return (x & ~HD) | (hd & HD); }
     // lane content of a channel word / of a fresh frame's message word: v2c(0) = channel value
     // (ArrayLDPC_Decoder.cpp:45-61), carrying that value's hard decision
     __device__ static __forceinline__ uint32_t llr_lane(int val, bool &bad)
@@ -211,7 +218,7 @@ struct Packed16 {
         uint32_t x = 4u * mn + ud;               // 4*(mn + u(diff)), lanes < 2^16
         // x - us on the FMA pipe (the ALU pipe is the bound resource); every lane stays >= 0
         asm("mad.lo.u32 %0, %1, 0xffffffff, %0;" : "+r"(x) : "r"(us));
-        return x >> 2;  // low two bits of every lane are zero (IMAD.HI here, 2 FMA slots for 1 ALU slot, measured slower)
+        return x >> 2;  // low two bits of every lane are zero (IMAD.HI here, 2 FMA slots for 1 ALU slot: 4 - 7 % slower on all codes)
     }
     __device__ static __forceinline__ uint32_t neg_c2v(uint32_t o, uint32_t inv)
     {
@@ -237,14 +244,46 @@ struct Packed16 {
     // yields |post + (-c2v)| >= CLAMP - (2^13+9) > 2^13, so the message guard below catches it,
     // and CLAMP + 2^13 + 9 < 2^15 keeps the packed add from wrapping.
     static constexpr int CLAMP = 24000;
+    static constexpr uint32_t CLAMP2 = 0x5dc05dc0u, NCLAMP2 = 0xa240a240u;  // +CLAMP / -CLAMP in both lanes
     template <int D> __device__ static __forceinline__ uint32_t post_word(const Acc &a, uint32_t &hd)
     {
         int lo = a.lo, hi = a.hi;
         // D <= 2: |post| <= LLR_LIMIT-1 + 2*(2^13+19) and |post + (-c2v)| stay below 2^15 (see LLR_LIMIT)
-        if (D > 2) { lo = max(min(lo, CLAMP), -CLAMP); hi = max(min(hi, CLAMP), -CLAMP); }
-        const uint32_t pw = __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
-        hd = (__vadd2(pw, 0xffffffffu) >> 1) & HD;  // sign of post-1 per lane, moved to bit 14
+        uint32_t pw;
+        if (D > 2) {
+            // saturating pack (I2IP), then +-CLAMP on both lanes at once: three instructions for five
+            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(pw) : "r"(hi), "r"(lo));
+            pw = __vmaxs2(__vmins2(pw, CLAMP2), NCLAMP2);
+        } else {
+            pw = __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
+        }
+        hd = __vadd2(pw, 0xffffffffu) >> 1;  // the users mask with HD  // sign of post-1 per lane, moved to bit 14
         return pw;
+    }
+    // posterior word of a degree-D variable from its channel word and the D stored words (-c2v)
+    template <int D> __device__ static __forceinline__ uint32_t posterior(uint32_t lx, const uint32_t *x, uint32_t &hd)
+    {
+        // The 32-bit sums cost two IDP per word; words are first added in the lanes as far as a lane holds them
+        // (|LLR| < LLR_LIMIT, |c2v| <= C2V_MAX = 2^13 + 19, see LLR_LIMIT).
+        if (D <= 3) {
+            // |LLR| + 3 * C2V_MAX < 2^15: the whole sum stays in the lanes
+            static_assert(LLR_LIMIT - 1 + 3 * (LIMIT + 19) < (1 << 15), "degree-3 posterior leaves its lane");
+            uint32_t s = x[0];
+#pragma unroll
+            for (int j = 1; j < D; ++j) s = __vadd2(s, x[j]);
+            const uint32_t pw = __vadd2(__vadd2(lx, ~s), 0x00010001u);  // lx - s per lane
+            hd = __vadd2(pw, 0xffffffffu) >> 1;  // the users mask with HD
+            return pw;
+        }
+        Acc acc = acc_init(lx);
+#pragma unroll
+        for (int j = 0; j < D; j += 3) {  // three words at a time: 3 * C2V_MAX < 2^15
+            uint32_t s = x[j];
+            if (j + 1 < D) s = __vadd2(s, x[j + 1]);
+            if (j + 2 < D) s = __vadd2(s, x[j + 2]);
+            acc_sub(acc, s);
+        }
+        return post_word<D>(acc, hd);
     }
     __device__ static __forceinline__ uint32_t v2c_signmag(uint32_t post, uint32_t nc)
     {
@@ -272,7 +311,7 @@ struct Packed16 {
     // channel lanes stay below LLR_LIMIT < 2^13 in magnitude, so bit 14 of a lane is a copy of its sign bit and
     // can carry the hard decision of the variable's last posterior (see Scalar32)
     __device__ static __forceinline__ uint32_t llr_restore(uint32_t x) { return (x & ~HD) | ((x >> 1) & HD); }
-    __device__ static __forceinline__ uint32_t llr_with_hd(uint32_t x, uint32_t hd) { return (x & ~HD) | hd; }
+    __device__ static __forceinline__ uint32_t llr_with_hd(uint32_t x, uint32_t hd) { return (x & ~HD) | (hd & HD); }
     // Channel values are admitted below LLR_LIMIT, slightly under 2^13, so that the unclamped posterior of a
     // degree <= 2 variable cannot wrap its lane: LLR_LIMIT-1 + 2*C2V_MAX + C2V_MAX < 2^15, where
     // C2V_MAX = 2^13-1 + 20 bounds every check output (each sxor adds at most 10 to the smaller magnitude).
@@ -621,13 +660,9 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uin
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
         lx[i] = T::llr_restore(llr[(w + i) * n + v]);
-        typename T::Acc acc = T::acc_init(lx[i]);
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            x[i][j] = *reinterpret_cast<uint32_t *>(base + i * stride + off[j]);
-            T::acc_sub(acc, x[i][j]);
-        }
-        pw[i] = T::template post_word<D>(acc, hd[i]);
+        for (int j = 0; j < D; ++j) x[i][j] = *reinterpret_cast<uint32_t *>(base + i * stride + off[j]);
+        pw[i] = T::template posterior<D>(lx[i], x[i], hd[i]);
         guard[i] = ACC ? gacc[i] : 0u;
     }
 #pragma unroll
@@ -635,11 +670,11 @@ __device__ __forceinline__ void variable_words(const KParams &p, Ctrl *ctrl, uin
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
             const uint32_t a = T::v2c_signmag(pw[i], x[i][j]);
-            *reinterpret_cast<uint32_t *>(base + i * stride + off[j]) = a | hd[i];
+            *reinterpret_cast<uint32_t *>(base + i * stride + off[j]) = a | (hd[i] & T::HD);
             x[i][j] = a;
             if (j + 1 < D) {
                 const uint32_t b = T::v2c_signmag(pw[i], x[i][j + 1]);
-                *reinterpret_cast<uint32_t *>(base + i * stride + off[j + 1]) = b | hd[i];
+                *reinterpret_cast<uint32_t *>(base + i * stride + off[j + 1]) = b | (hd[i] & T::HD);
                 x[i][j + 1] = b;
                 guard[i] = or3(guard[i], a, b);
             } else {
@@ -729,7 +764,7 @@ __device__ __forceinline__ void variable_node_any(const KParams &p, Ctrl *ctrl, 
             uint32_t *q = &ew[p.vedge[(size_t)j * n + v]];
             const uint32_t a = T::v2c_signmag(pw, *q);
             guard |= a;
-            *q = a | hd;
+            *q = a | (hd & T::HD);
         }
         if (T::guard_hit(guard)) atomicOr(&gflag[w], T::guard_lanes(guard));
         llr[(size_t)w * n + v] = T::llr_with_hd(lx, hd);
