@@ -33,21 +33,23 @@ struct KernelChoice {
     int ws = 0, ts = 0;
     int max_threads = 0;
     int ni = 1;
+    int cs = 1;  // checks of one word set interleaved per thread (CS of the kernel)
     int ctas_per_sm = 1;
     bool cdeg_in_smem = false, vdeg_in_smem = false;
 };
 
 template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA = 0, int ARRP = 0, unsigned VMASK = 0xffffffffu,
-          unsigned CMASK = 0xffffffffu, int WS16 = 0, int WS32 = 0, int TS = 0>
+          unsigned CMASK = 0xffffffffu, int WS16 = 0, int WS32 = 0, int TS = 0, int CS = 1>
 static KernelChoice make_choice()
 {
     KernelChoice k;
-    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA, ARRP, VMASK, CMASK, 0, 0>;
+    k.fn = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA, ARRP, VMASK, CMASK, 0, 0, CS>;
+    k.cs = CS;
     // word sets per CTA the plan arrives at without overrides (packed and int32 kernels have the same count: a word set
     // is E + n words either way)
     constexpr int WS = T::LANES == 2 ? WS16 : WS32;
     if (WS > 0) {
-        k.fn_ws = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA, ARRP, VMASK, CMASK, WS, TS>;
+        k.fn_ws = decode_kernel<T, DC, REG, DV, NI, MAXT, NCTA, M, N, EA, ARRP, VMASK, CMASK, WS, TS, CS>;
         k.ws = WS;
         k.ts = TS;
     }
@@ -102,11 +104,15 @@ template <class T> static KernelChoice pick_kernel(const ldpc_code &c)
     }
     if (regular && vregular && c.dc_max == 47 && c.dv_max == 24 && c.m == 1128 && c.n == 2209 && is_forward_array(c, 47))  // array p47 r24
     {
-        // One 221 KB word set per SM.  A 512-thread bound gives the chains 128 registers (no spills); make_plan then
-        // picks 384 threads: 12 warps x 3 passes cover the 36 warp-loads of checks exactly, three warps per scheduler
-        // (0.60 M frames/s against 0.53 M for 576 threads / 96 registers, 0.58 M for 640).  LDPC_A24_640=1: the 96-register build.
+        // One 221 KB word set per SM, 384 threads: 12 warps, three per scheduler.  Every thread interleaves three checks
+        // (c, c + 376, c + 752: CS = 3, 164 registers, no spills), so the 1128 checks are one pass of 376 threads with
+        // three dependency chains each: +2 % over one check per thread in three passes (128 registers), which
+        // LDPC_A24_SPLIT=1 keeps; two checks per thread on 288 threads: -21 %; 576 threads / 96 registers: -15 %
+        // (profiles/r02/launch_shape_sweep.txt).  LDPC_A24_640=1: the 96-register build.
         if (getenv("LDPC_A24_640")) return make_choice<T, 47, true, 24, 1, 640, 1, 1128, 2209, 0, 47>();
-        return make_choice<T, 47, true, 24, 1, 512, 1, 1128, 2209, 0, 47, 0xffffffffu, 0xffffffffu, 1, 1, 384>();
+        if (const char *sp = getenv("LDPC_A24_SPLIT"))
+            if (atoi(sp) == 1) return make_choice<T, 47, true, 24, 1, 512, 1, 1128, 2209, 0, 47, 0xffffffffu, 0xffffffffu, 1, 1, 384>();
+        return make_choice<T, 47, true, 24, 1, 384, 1, 1128, 2209, 0, 47, 0xffffffffu, 0xffffffffu, 1, 1, 384, 3>();
     }
     if (regular && vregular && c.dc_max == 28 && c.dv_max == 4 && c.m == 316 && c.n == 2212)          // cut79
         return make_choice<T, 28, true, 4, 1, 640, 2, 316, 2212, 0, 0, 0xffffffffu, 0xffffffffu, 2, 2, 640>();
@@ -204,7 +210,7 @@ static int make_plan(const ldpc_decoder &d, int lanes, KernelChoice k, int want_
     if (W < k.ni) { set_error("the word sets one thread interleaves do not fit in shared memory"); return LDPC_ERR_UNSUPPORTED; }
     W -= W % k.ni;  // the check phase walks the word sets in groups of NI
     // CTA size: best check-phase lane efficiency, ties to the larger CTA
-    const int items = (W / k.ni) * c.m;
+    const int items = (W / k.ni) * (c.m / k.cs);
     int best_t = 0; double best_e = -1;
     for (int t = 128; t <= k.max_threads; t += 32) {
         int passes = (items + t - 1) / t;

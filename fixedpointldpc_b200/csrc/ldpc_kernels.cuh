@@ -550,7 +550,9 @@ __device__ __forceinline__ uint32_t check_node_any(uint32_t *e, int m, int d)
 // thread per (word-set group, check); the syndrome bits are OR-ed into fail[word set], one shared atomic per warp
 // CMASK: check degrees that get an exact body (bit d); a named irregular code lists its own, which keeps the hot
 // code small (the 802.11 code has degrees 7 and 8 only -- fifteen exact bodies are 5 000 instructions)
-template <class T, int DC, bool REG, int NI, unsigned CMASK>
+// CS: (regular codes, NI == 1) checks of one word set per thread, interleaved like the NI word sets are: check c,
+// c + m/CS, ... -- instruction-level parallelism for a CTA that holds a single word set
+template <class T, int DC, bool REG, int NI, unsigned CMASK, int CS>
 __device__ __forceinline__ void check_phase(const KParams &p, uint32_t *fail, uint32_t *edge, const uint8_t *cdeg_s,
                                             int items, int m, int E, int W, int nthreads)
 {
@@ -609,10 +611,20 @@ __device__ __forceinline__ void check_phase(const KParams &p, uint32_t *fail, ui
         uint32_t fb[NI];
 #pragma unroll
         for (int j = 0; j < NI; ++j) fb[j] = 0u;
-        if (valid) {
+        if (valid && CS == 1) {
             wg = (int)__umulhi((uint32_t)i, p.inv_m);
             const int c = i - wg * m;
             check_nodes<T, DC, NI>(edge + (size_t)(wg * NI) * E + c, m, E, fb);
+        }
+        if (valid && CS > 1) {
+            static_assert(CS == 1 || NI == 1, "check split needs one word set per thread");
+            const int mh = m / CS;
+            wg = i / mh;
+            const int c = i - wg * mh;
+            uint32_t fs[CS];
+            check_nodes<T, DC, CS>(edge + (size_t)wg * E + c, m, mh, fs);
+#pragma unroll
+            for (int j = 0; j < CS; ++j) fb[0] |= fs[j];
         }
         if (one_group) {
 #pragma unroll
@@ -1167,6 +1179,7 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
 //   WS, TS  word sets per CTA and CTA size as compile-time constants (0: p.W / blockDim.x): the named codes run with the
 //        shape their plan computes; the loops over word sets and over the CTA's passes then have one shape and constant
 //        trip counts (measured +3 to +6 % on all four codes, profiles/r02/launch_shape_sweep.txt)
+//   CS   regular codes with NI == 1: checks of one word set interleaved per thread (m is a multiple of CS)
 //   MAXT, NCTA  launch bounds: CTA size and co-resident CTAs per SM.  Co-resident CTAs drift out of phase, so
 //        one's latency-bound variable phase overlaps the other's ALU-bound check phase.
 //
@@ -1180,7 +1193,7 @@ __device__ __forceinline__ uint32_t stop_decision(const KParams &p, Ctrl *ctrl, 
 // so a frame that stops costs one check phase more than the reference executes, and a converged frame is
 // found by the same two barriers per trip that the phases need anyway.
 // ------------------------------------------------------------------------------------------
-template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA, int ARRP, unsigned VMASK, unsigned CMASK, int WS, int TS>
+template <class T, int DC, bool REG, int DV, int NI, int MAXT, int NCTA, int M, int N, int EA, int ARRP, unsigned VMASK, unsigned CMASK, int WS, int TS, int CS = 1>
 __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constant__ KParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -1209,7 +1222,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
     }
     __syncthreads();
 
-    const int items = (W / NI) * m;  // (word-set group, check)
+    const int items = (W / NI) * (m / CS);  // (word-set group, check)
 #ifdef LDPC_PHASE_TIMING
     long long t_phase[4] = {0, 0, 0, 0}, t_mark = clock64();
 #define LDPC_MARK(k) do { long long t_now = clock64(); t_phase[k] += t_now - t_mark; t_mark = t_now; } while (0)
@@ -1236,7 +1249,7 @@ __global__ void __launch_bounds__(MAXT, NCTA) decode_kernel(const __grid_constan
         else variable_phase<T, DV, false, REGV, VMASK>(p, ctrl, ctrl->gflag[buf], edge, llr, W, n, E, vdeg_s, nthreads);
         __syncthreads();
         LDPC_MARK(1);
-        check_phase<T, DC, REG, NI, CMASK>(p, ctrl->fail[buf], edge, cdeg_s, items, m, E, W, nthreads);
+        check_phase<T, DC, REG, NI, CMASK, CS>(p, ctrl->fail[buf], edge, cdeg_s, items, m, E, W, nthreads);
         __syncthreads();
         LDPC_MARK(2);
         fin = stop_decision<T>(p, ctrl, W, trip, buf);
