@@ -457,6 +457,57 @@ def bench_mc(ctx, steps):
             "ms_per_round": float(ms.item()) / steps}
 
 
+def bench_encoder(ctx, steps):
+    """Encoder leg (SURVEY 8 row N2): FP_Encoder::encode batched on the GPU for the array p47 r5 generator derived from H.
+    Device-timed on resident message words, and end to end through ldpc_encode_batch (host bytes in, packed codewords
+    out); every codeword of one batch is checked against H on the host (numpy), a sample against the host encoder."""
+    import numpy as np
+    torch, fp = ctx["torch"], ctx["fp"]
+    dev, stream, local = ctx["dev"], ctx["stream"], ctx["local"]
+    code = fp.codes.NAMED["a5"]()
+    gen = fp.Generator(code=code)
+    frames, kw, nw = 1 << 18, (gen.k + 31) // 32, (gen.n + 31) // 32
+    rng = np.random.default_rng(20261019)
+    info = rng.integers(0, 256, (frames, (gen.k + 7) // 8), dtype=np.uint8)
+    if gen.k % 8:
+        info[:, -1] &= (1 << (gen.k % 8)) - 1
+    words = np.zeros((frames, kw * 4), np.uint8)
+    words[:, :info.shape[1]] = info
+    d_info = torch.from_numpy(words.view(np.int32).reshape(frames, kw)).to(dev)
+    d_cw = torch.zeros((frames, nw), dtype=torch.int32, device=dev)
+    for _ in range(3):
+        gen.encode_batch_device(d_info.data_ptr(), frames, d_cw.data_ptr(), device=local, cuda_stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        gen.encode_batch_device(d_info.data_ptr(), frames, d_cw.data_ptr(), device=local, cuda_stream=stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # all codewords of the batch against H; a sample against the host encoder (FP_Encoder::encode on the CPU)
+    cw = d_cw.cpu().numpy().view(np.uint32)
+    checked = 1 << 14
+    bits = np.unpackbits(cw[:checked].view(np.uint8), axis=1, bitorder="little")[:, :gen.n]
+    _, cdeg, _, clist = code.tables()
+    clist = np.asarray(clist).reshape(code.m, -1)
+    syn = np.zeros((checked, code.m), np.uint8)
+    for k in range(clist.shape[1]):
+        syn ^= np.where(k < np.asarray(cdeg), bits[:, np.maximum(clist[:, k], 0)], 0).astype(np.uint8)
+    host_mismatch = sum(int((gen.encode(info[f].tobytes()) != bits[f]).any()) for f in range(0, checked, checked // 64))
+    t0 = time.perf_counter()
+    out = gen.encode_batch(info[: 1 << 16], device=local)
+    e2e_s = time.perf_counter() - t0
+    bytes_per_frame = 4 * (kw + nw)
+    return {"code": "a5", "api": "ldpc_encode_batch_device (resident message words -> packed codewords)", "frames_per_launch": frames,
+            "ms_per_launch": ms, "frames_per_s": frames / (ms * 1e-3), "value": frames * gen.k / (ms * 1e-3) / 1e9, "unit": "info Gbit/s",
+            "hbm_GBps": frames * bytes_per_frame / (ms * 1e-3) / 1e9, "algorithmic_bytes_per_frame": bytes_per_frame,
+            "codewords_checked_against_H": checked, "codewords_failing_H": int(syn.any(axis=1).sum()),
+            "host_encoder_mismatches_in_64": host_mismatch,
+            "e2e": {"api": "ldpc_encode_batch (host bytes in, packed codewords out, pageable memory)", "frames": 1 << 16,
+                    "value": (1 << 16) * gen.k / e2e_s / 1e9, "unit": "info Gbit/s", "identical_to_device_run": bool((out == cw[: 1 << 16]).all())}}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -500,6 +551,7 @@ def run_gpu_arm(args):
             if c != args.code:
                 others[c] = bench_code(ctx, c, max(3, args.steps // 4), 3, False)
         mc = bench_mc(ctx, max(3, args.steps // 4))
+        enc = bench_encoder(ctx, max(3, args.steps // 4)) if rank == 0 else None
     if "p" in pool_box:
         pool_box["p"].close()
     if rank == 0:
@@ -513,6 +565,7 @@ def run_gpu_arm(args):
         if not args.only:
             line["codes"] = others
             line["mc"] = mc
+            line["encoder"] = enc
             line["gpu_launches"] = head["gpu_launches"]  # launches inside the headline's timed region
         print(json.dumps(line))
     if world > 1:

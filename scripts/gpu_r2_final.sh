@@ -2,7 +2,7 @@
 # round 2, call R: final ncu captures of the shipped kernels (summaries only), then whole suite + smoke + both bench arms
 set -x
 cd "$GRAFT_REPO_ROOT" || exit 1
-O=gpurun_out/r2r; mkdir -p $O
+O=gpurun_out/r2u; mkdir -p $O
 for c in wifi a5 c79 a24; do
   timeout 400 ncu --set full --import-source on --clock-control none -k regex:decode_kernel -s 3 -c 1 -o $O/prof_${c} -f \
     python bench.py --code $c --only --precision 16 --steps 1 --warmup 3 --no-cpu --frames 16384 > $O/ncu_${c}.log 2>&1
@@ -23,4 +23,6 @@ cp gpurun_out/parity_at_scale_last.txt gpurun_out/facade_latency.txt $O/ 2>/dev/
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"
 timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > $O/bench_reference.json 2> $O/bench_reference.err; echo "ref rc=$?"
 timeout 900 python bench.py --steps 20 --warmup 5 > $O/bench_full.json 2> $O/bench_full.err; echo "bench rc=$?"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench_wifi_r2.csv \
+    python bench.py --only --no-cpu --steps 5 --warmup 3 > $O/ncu_launches.log 2>&1
 du -sh $O
