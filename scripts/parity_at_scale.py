@@ -20,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-POINTS = {"wifi": (2.0, 0.5), "a5": (4.5, 2.0), "c79": (4.5, 2.0), "a24": (6.0, 3.0)}
+# operating point, a point where every frame runs MAX_ITER, and a high-SNR point (pre-check hits, large channel values)
+POINTS = {"wifi": (2.0, 0.5, 9.0), "a5": (4.5, 2.0, 8.0), "c79": (4.5, 2.0, 8.0), "a24": (6.0, 3.0, 9.0)}
 PRECHECK = {"wifi": False, "a5": True, "c79": False, "a24": True}
 
 

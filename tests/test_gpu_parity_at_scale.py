@@ -1,4 +1,4 @@
-"""Full-state parity at the scale SURVEY.md 8(c) asks for (scripts/parity_at_scale.py): 100 000 frames per code at two
+"""Full-state parity at the scale SURVEY.md 8(c) asks for (scripts/parity_at_scale.py): 100 000 frames per code at three
 Eb/N0 points (array p47 r24: 10 000), CUDA engine through the C ABI with parity-mode outputs against the CPU oracle on
 all host cores; iteration counts, decoded bits, posteriors and final messages compared frame by frame through CRC-32
 digests.  About 100 s on the B200 box (16 host cores); LDPC_SCALE_FRAMES shrinks it."""
