@@ -245,3 +245,26 @@ def test_philox_fer_agrees_with_reference_stream_within_confidence(fp, golden):
     # bit errors per failed frame are of the reference's order (2732 / 100)
     assert 10 < out["bit_errors"] / max(1, out["frame_errors"]) < 60
     dec.close()
+
+
+def test_array_philox_rates_agree_with_reference_stream_within_confidence(fp, golden):
+    """BASELINE config 5 runs the array p47 r5 waterfall on the Philox stream; its rates must be compatible with the
+    reference noise stream's known answer at 4.5 dB (993 frame errors in 20 000 frames):
+    two-sample z-test on the frame error rate (|z| < 3.5), mean iteration count within 1 %, bit errors per failed
+    frame of the reference's order (27 011 / 993)."""
+    code = fp.codes.array_p47_r5()
+    dec = fp.Decoder(code, precheck=True)
+    snr = 2 * 10 ** (4.5 / 10) * code.rate
+    ref = dec.mc_run(20000, snr, stream=fp.STREAM_REFERENCE, seed=123456789, codeword=golden["a5_codeword"],
+                     info_index=golden["a5_info_index"], want_frame_err=False)
+    assert ref["frame_errors"] == 993
+    frames = 400000
+    out = dec.mc_run(frames, snr, stream=fp.STREAM_PHILOX, seed=55, codeword=golden["a5_codeword"],
+                     info_index=golden["a5_info_index"], want_frame_err=False)
+    p1, n1, p2, n2 = out["frame_errors"] / frames, frames, 993 / 20000, 20000
+    pooled = (out["frame_errors"] + 993) / (n1 + n2)
+    z = (p1 - p2) / np.sqrt(pooled * (1 - pooled) * (1 / n1 + 1 / n2))
+    assert abs(z) < 3.5, (out["frame_errors"], z)
+    assert abs(out["iter_sum"] / frames - ref["iter_sum"] / 20000) < 0.01 * ref["iter_sum"] / 20000 + 0.05
+    assert 0.8 * 27011 / 993 < out["bit_errors"] / out["frame_errors"] < 1.2 * 27011 / 993
+    dec.close()
